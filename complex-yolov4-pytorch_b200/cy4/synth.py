@@ -1,0 +1,57 @@
+"""Seeded synthetic inputs for the hot path.  numpy PCG64 streams are
+stable across machines, so tests, golden fixtures and bench.py all see the same data."""
+import math
+
+import numpy as np
+
+
+def make_pairs(n, seed=7, grid=76.0, disjoint_frac=0.0):
+    """n (pred, target) rotated-box pairs in grid units, as YoloLayer.build_targets feeds
+    iou_pred_vs_target_boxes (reference src/models/yolo_layer.py:134).  Returns two [n,6] fp32
+    arrays (x, y, w, l, im, re)."""
+    rng = np.random.default_rng(seed)
+    tx = rng.uniform(0, grid, n); ty = rng.uniform(0, grid, n)
+    tw = rng.uniform(1.25, 3.75, n); tl = rng.uniform(1.9, 8.1, n)
+    tyaw = rng.uniform(-math.pi, math.pi, n)
+    tgt = np.stack([tx, ty, tw, tl, np.sin(tyaw), np.cos(tyaw)], 1)
+    px = tx + rng.uniform(-0.5, 0.5, n); py = ty + rng.uniform(-0.5, 0.5, n)
+    pw = tw * np.exp(rng.normal(0, 0.3, n)); pl = tl * np.exp(rng.normal(0, 0.3, n))
+    pim = np.sin(tyaw) + rng.normal(0, 0.3, n); pre = np.cos(tyaw) + rng.normal(0, 0.3, n)
+    if disjoint_frac > 0:
+        far = rng.uniform(0, 1, n) < disjoint_frac
+        px = np.where(far, px + rng.choice([-1, 1], n) * rng.uniform(12, 30, n), px)
+        py = np.where(far, py + rng.choice([-1, 1], n) * rng.uniform(12, 30, n), py)
+    pred = np.stack([px, py, pw, pl, pim, pre], 1)
+    return pred.astype(np.float32), tgt.astype(np.float32)
+
+
+def make_targets(batch, per_image=5, seed=4321, img_size=608, strides=(8, 16, 32), total=None):
+    """[nT,8] fp32 targets (image, class, x, y, w, l, im, re) with x..l normalised to [0,1), as
+    collate_fn emits (reference src/data_process/kitti_dataset.py:216-233).  (image, cell) is
+    distinct at every stride so target assignment has no duplicate cells.  total pins nT."""
+    rng = np.random.default_rng(seed)
+    n = total if total is not None else batch * per_image
+    rows, used = [], set()
+    k = 0
+    while len(rows) < n:
+        b = (len(rows) // per_image) % batch if total is None else int(rng.integers(0, batch))
+        cls = int(rng.integers(0, 3))
+        x = rng.uniform(0.05, 0.95); y = rng.uniform(0.05, 0.95)
+        cells = [(b, s, int(np.float32(x) * np.float32(img_size // s)), int(np.float32(y) * np.float32(img_size // s)))
+                 for s in strides]
+        k += 1
+        if any(c in used for c in cells) and k < 100000:
+            continue
+        used.update(cells)
+        w = rng.uniform(10, 30) / img_size; l = rng.uniform(15, 65) / img_size
+        yaw = rng.uniform(-math.pi, math.pi)
+        rows.append([b, cls, x, y, w, l, math.sin(yaw), math.cos(yaw)])
+    t = np.asarray(rows, dtype=np.float32)
+    return t[np.argsort(t[:, 0], kind="stable")]
+
+
+def make_bev(batch, seed=1234, img_size=608, channels=3):
+    """[B,3,608,608] fp32 in [0,1) -- the BEV stand-in BASELINE.json names ("synthetic BEV")."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.rand(batch, channels, img_size, img_size, generator=g, dtype=torch.float32)

@@ -1,0 +1,42 @@
+"""Import the UNMODIFIED reference modules from /root/reference/src (build container only).
+
+TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box: nothing that runs
+there may call this.  Used by oracle/gen_golden.py and by the optional live cross-checks in
+tests/ (skipped when the reference tree is absent).
+"""
+import importlib
+import os
+import sys
+
+REF_SRC = "/root/reference/src"
+
+
+def available():
+    return os.path.isdir(REF_SRC)
+
+
+def load():
+    """Returns a dict of the reference modules on the hot path."""
+    from . import shapely_standin
+    kind = shapely_standin.install()
+    # The reference imports its own top-level packages `models`, `utils`.  Make sure ours
+    # (complex-yolov4-pytorch_b200/) do not shadow them while loading, then restore.
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.pop(k) for k in list(sys.modules)
+                  if k in ("models", "utils") or k.startswith("models.") or k.startswith("utils.")}
+    sys.path = [REF_SRC] + [p for p in sys.path if "complex-yolov4-pytorch_b200" not in p]
+    try:
+        mods = {
+            "clip": importlib.import_module("utils.cal_intersection_rotated_boxes"),
+            "iou": importlib.import_module("utils.iou_rotated_boxes_utils"),
+            "yolo": importlib.import_module("models.yolo_layer"),
+            "darknet": importlib.import_module("models.darknet2pytorch"),
+        }
+    finally:
+        for k in list(sys.modules):
+            if k in ("models", "utils") or k.startswith("models.") or k.startswith("utils."):
+                sys.modules["_ref_" + k] = sys.modules.pop(k)
+        sys.modules.update(saved_mods)
+        sys.path = saved_path
+    mods["shapely_kind"] = kind
+    return mods
