@@ -1,0 +1,120 @@
+/*
+ * cy4.h -- C-ABI of libcy4.so, the B200 (sm_100a) implementation of the Complex-YOLOv4 training
+ * hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * The reference (maudzung/Complex-YOLOv4-Pytorch) is pure Python and has no FFI of its own
+ * (SURVEY.md F1); the boundary a maintainer binds is therefore the set of reference *functions*
+ * each entry point replaces, cited per declaration as file:line under /root/reference/src.
+ * INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every pointer is a BORROWED device pointer (cudaMalloc'd / torch-owned) unless marked host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions return 0 on success, <0 on error; cy4_last_error() returns a thread-local,
+ *     NUL-terminated description of the most recent failure on the calling thread;
+ *   - no function synchronises the device, allocates caller-visible memory or throws;
+ *   - all entry points are re-entrant across threads.
+ */
+#ifndef CY4_H
+#define CY4_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CY4_VERSION 100
+
+#if defined(CY4_BUILD) && defined(__GNUC__)
+#define CY4_API __attribute__((visibility("default")))
+#else
+#define CY4_API
+#endif
+
+/* flags for the rotated-IoU entry points */
+#define CY4_F_GIOU 1u /* reference clipper + convex-hull GIoU term (GIoU=True); else exact-intersection IoU */
+
+CY4_API int cy4_version(void);
+CY4_API const char *cy4_last_error(void);
+/* 0 if a CUDA device of compute capability 10.x is usable by this library, <0 otherwise (host call). */
+CY4_API int cy4_device_ok(void);
+
+/* ---- rotated-box geometry -------------------------------------------------------------------
+ * utils/iou_rotated_boxes_utils.py:98-142  iou_pred_vs_target_boxes (element-wise pairs), with
+ * utils/cal_intersection_rotated_boxes.py:42-96 (intersection_area / PolyArea2D) inside.
+ * pred6/tgt6: [n,6] fp32 rows (x, y, w, l, im, re).  iou, term: [n] fp32; term is the summand of
+ * giou_loss (1 - iou + (C-U)/C with GIoU, 1 - iou without).  gpred6 (optional, may be NULL):
+ * [n,6] d term / d pred under the reference's autograd semantics, multiplied by
+ * gterm[k] when gterm != NULL (else by 1). */
+CY4_API int cy4_rgiou_pairs(const float *pred6, const float *tgt6, int64_t n, uint32_t flags,
+                    float *iou, float *term, const float *gterm, float *gpred6, void *stream);
+
+/* Sequential-order (reference `giou_loss += term`, :133) fp32 sum of term[0..n) into out[0]. */
+CY4_API int cy4_sum_f32_seq(const float *term, int64_t n, float *out, void *stream);
+
+/* utils/iou_rotated_boxes_utils.py:34-61 get_corners_vectorize: boxes5 [n,5] (x,y,w,l,yaw) -> [n,4,2]. */
+CY4_API int cy4_corners(const float *x, const float *y, const float *w, const float *l, const float *yaw,
+                int64_t n, float *corners /* [n,4,2] */, void *stream);
+
+/* utils/cal_intersection_rotated_boxes.py:42-96: intersection_area of n quad pairs ([n,4,2] each). */
+CY4_API int cy4_quad_intersection_area(const float *rect1, const float *rect2, int64_t n, float *area, void *stream);
+/* utils/cal_intersection_rotated_boxes.py:93-96: PolyArea2D of one polygon pts [k,2], k <= 16. */
+CY4_API int cy4_poly_area(const float *pts, int k, float *area, void *stream);
+
+/* utils/iou_rotated_boxes_utils.py:64-95: get_polygons_areas_fix_xy + iou_rotated_boxes_targets_vs_anchors.
+ * anchors4 [nA,4], tgt4 [nT,4] rows (w, l, im, re), both placed at (100,100); ious [nA,nT]. */
+CY4_API int cy4_anchor_iou(const float *anchors4, int nA, const float *tgt4, int64_t nT, float *ious, void *stream);
+
+/* ---- YOLO head --------------------------------------------------------------------------------
+ * models/yolo_layer.py:144-253 YoloLayer.forward and :69-142 build_targets.
+ * The raw head tensor is addressed through element strides so both the reference's NCHW layout and
+ * the engine's NHWC layout work:  value(b, c, y, x) = pred[b*sB + c*sC + y*sH + x*sW].          */
+typedef struct cy4_yolo_desc {
+    int32_t B, G, nA, nC;         /* batch, grid size, anchors per cell, classes (nC <= 32) */
+    int64_t sB, sC, sH, sW;       /* element strides of the raw head tensor */
+    float img_size;               /* 608: stride = img_size / G (yolo_layer.py:56) */
+    float ignore_thresh;          /* 0.7 (yolo_layer.py:119, strict >) */
+    uint32_t use_giou;            /* 1: total = 3.54 giou + 3.54 eular + 64.3 obj + 37.4 cls (:213-215) */
+    uint32_t reserved;
+} cy4_yolo_desc;
+
+#define CY4_YOLO_NMETRICS 18      /* order of yolo_layer.py:232-251 */
+
+/* bytes of scratch cy4_yolo_loss_* need for (desc, nT); contents opaque, must persist fwd -> bwd */
+CY4_API size_t cy4_yolo_workspace_bytes(const cy4_yolo_desc *d, int64_t nT);
+
+/* Decode only (targets=None): output [B, nA*G*G, 7+nC] rows (x,y,w,l in pixels, im, re, conf, cls..),
+ * row order anchor-major then gj then gi (yolo_layer.py:184-189). anchors4 [nA,4] = (w/stride, h/stride, im, re). */
+CY4_API int cy4_yolo_decode(const cy4_yolo_desc *d, const float *pred, const float *anchors4, float *output, void *stream);
+
+/* Decode + target assignment + losses + metrics in one pass over the head tensor.
+ * targets8 [nT,8] rows (image, class, x, y, w, l, im, re) normalised to [0,1) (may be NULL iff nT==0).
+ * loss[1]; metrics[18]; status[1] int32: bit0 = a target indexed outside the grid/batch
+ * (the reference raises IndexError there; such targets are skipped). */
+CY4_API int cy4_yolo_loss_fwd(const cy4_yolo_desc *d, const float *pred, const float *anchors4,
+                      const float *targets8, int64_t nT, float *output /* may be NULL */,
+                      float *loss, float *metrics, int32_t *status, void *workspace, void *stream);
+
+/* d loss / d pred, scaled by gloss[0]; dpred uses dense strides (dsB, dsC, dsH, dsW) and is fully
+ * overwritten for the nA*(7+nC) head channels. */
+CY4_API int cy4_yolo_loss_bwd(const cy4_yolo_desc *d, const float *pred, const float *anchors4,
+                      const float *targets8, int64_t nT, const float *gloss, const void *workspace,
+                      float *dpred, int64_t dsB, int64_t dsC, int64_t dsH, int64_t dsW, void *stream);
+
+/* models/yolo_layer.py:69-142 build_targets with its 13 dense outputs (API parity; the fused
+ * loss above does not materialise them).  pred_boxes [B,nA,G,G,6], pred_cls [B,nA,G,G,nC] contiguous.
+ * Dense outputs are [B,nA,G,G] (tcls [B,nA,G,G,nC]); masks are uint8 0/1; giou_loss[1] is already
+ * divided by nT.  idx (optional) [5,nT] int64: b, best_n, gj, gi, label. */
+CY4_API int cy4_build_targets(const cy4_yolo_desc *d, const float *pred_boxes, const float *pred_cls,
+                      const float *targets8, int64_t nT, const float *anchors4,
+                      float *iou_scores, float *giou_loss, float *class_mask, uint8_t *obj_mask,
+                      uint8_t *noobj_mask, float *tx, float *ty, float *tw, float *th, float *tim,
+                      float *tre, float *tcls, float *tconf, int64_t *idx, int32_t *status,
+                      void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CY4_H */

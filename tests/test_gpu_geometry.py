@@ -1,0 +1,133 @@
+"""GPU: rotated-box kernels (through the C-ABI) against the golden vectors of the reference and
+against the CPU oracle on larger seeded sets."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# GIoU values: BASELINE.json tolerance 1e-4 (the reference's own fp32 noise floor).
+TOL = 1e-4
+
+
+def _run(pred, tgt, giou=True, grad=False):
+    from cy4 import geometry as cg
+    p = torch.tensor(pred, device="cuda", requires_grad=grad)
+    t = torch.tensor(tgt, device="cuda")
+    iou, term = cg.rgiou_pairs(p, t, giou)
+    g = None
+    if grad:
+        term.sum().backward()
+        g = p.grad.cpu().numpy()
+    return iou.cpu().numpy(), term.detach().cpu().numpy(), g
+
+
+def test_known_answers(golden):
+    g = golden("rgiou_pairs.npz")
+    iou, term, _ = _run(g["ka_pred"], g["ka_tgt"])
+    np.testing.assert_allclose(iou, g["ka_iou"], atol=2e-6)
+    np.testing.assert_allclose(term, g["ka_term"], atol=2e-6)
+    np.testing.assert_allclose(iou[:4], [0.366509, 0.2, 1.0, 1.0 / 3.0], atol=2e-6)
+    np.testing.assert_allclose(iou[4], 1.0000002, atol=1e-6)      # F5 quirk reproduced
+
+
+def test_pairs_vs_reference_golden(golden):
+    g = golden("rgiou_pairs.npz")
+    iou, term, grad = _run(g["pred"], g["tgt"], grad=True)
+    assert np.abs(iou - g["iou"]).max() <= TOL
+    assert np.abs(term - g["term"]).max() <= TOL
+    d = np.abs(grad - g["grad"])
+    assert (d / (np.abs(g["grad"]) + 1e-2)).max() < 5e-3
+
+
+def test_api_function_shapes(golden):
+    from cy4 import geometry as cg
+    g = golden("rgiou_pairs.npz")
+    p = torch.tensor(g["pred"][:64], device="cuda", requires_grad=True)
+    t = torch.tensor(g["tgt"][:64], device="cuda")
+    ious, loss = cg.iou_pred_vs_target_boxes(p, t, GIoU=True)
+    assert ious.shape == (64,) and loss.shape == (1,) and not ious.requires_grad
+    np.testing.assert_allclose(loss.item(), g["batch64_loss"][0], rtol=1e-5)
+    loss.backward()
+    np.testing.assert_allclose(p.grad.cpu().numpy(), g["batch64_grad"], atol=2e-5, rtol=5e-3)
+    with pytest.raises(NotImplementedError):
+        cg.iou_pred_vs_target_boxes(p, t, GIoU=True, CIoU=True)
+    with pytest.raises(AssertionError):
+        cg.iou_pred_vs_target_boxes(p, t[:3], GIoU=True)
+    e_i, e_l = cg.iou_pred_vs_target_boxes(p[:0], t[:0], GIoU=True)
+    assert e_i.numel() == 0 and float(e_l) == 0.0
+
+
+def test_shapely_path(golden):
+    g = golden("rgiou_pairs.npz")
+    n = len(g["shapely_iou"])
+    iou, term, grad = _run(g["pred"][:n], g["tgt"][:n], giou=False, grad=True)
+    np.testing.assert_allclose(iou, g["shapely_iou"], atol=1e-6)
+    np.testing.assert_allclose(grad, g["shapely_grad"], atol=1e-6, rtol=1e-3)
+
+
+@pytest.mark.parametrize("n,seed,disjoint", [(1, 0, 0.0), (127, 1, 0.1), (128, 2, 0.0), (100000, 7, 0.01)])
+def test_pairs_vs_oracle(n, seed, disjoint):
+    from cy4 import synth
+    from oracle import geometry as og
+    pred, tgt = synth.make_pairs(n, seed=seed, disjoint_frac=disjoint)
+    iou, term, grad = _run(pred, tgt, grad=True)
+    oi, ot, ogr = og.rgiou_pairs(pred, tgt, True, True)
+    assert np.abs(iou - oi).max() <= TOL
+    assert np.abs(term - ot).max() <= TOL
+    assert (np.abs(grad - ogr) / (np.abs(ogr) + 1e-2)).max() < 5e-3
+    assert (iou == oi).mean() > 0.85          # mostly bit-identical (libm vs CUDA trig last-ulp otherwise)
+
+
+def test_size_independent_properties():
+    """10^7 pairs (BASELINE.json bandwidth run): IoU in [0, 1+eps] for overlapping pairs, identical
+    boxes give IoU 1 / term 0, and the result does not depend on where in the batch a pair sits."""
+    from cy4 import synth
+    n = 10_000_000
+    pred, tgt = synth.make_pairs(n, seed=7)
+    p = torch.tensor(pred, device="cuda"); t = torch.tensor(tgt, device="cuda")
+    from cy4 import geometry as cg
+    iou, term = cg.rgiou_pairs(p, t, True)
+    assert torch.isfinite(iou).all() and torch.isfinite(term).all()
+    assert float(iou.min()) >= 0.0 and float(iou.max()) <= 1.0 + 1e-3
+    i2, t2 = cg.rgiou_pairs(t, t, True)
+    assert float((i2 - 1).abs().max()) < 2e-3 and float(t2.abs().max()) < 2e-3
+    perm = torch.randperm(n, device="cuda")
+    i3, t3 = cg.rgiou_pairs(p[perm], t[perm], True)
+    assert torch.equal(i3, iou[perm]) and torch.equal(t3, term[perm])
+
+
+def test_anchor_iou(golden):
+    from cy4 import geometry as cg
+    g = golden("anchor_iou.npz")
+    for G in (76, 38, 19):
+        a = torch.tensor(g[f"anchors_{G}"], device="cuda"); t = torch.tensor(g[f"tboxes_{G}"], device="cuda")
+        ap, aa = cg.get_polygons_areas_fix_xy(a)
+        tp, ta = cg.get_polygons_areas_fix_xy(t)
+        got = cg.iou_rotated_boxes_targets_vs_anchors(ap, aa, tp, ta).cpu().numpy()
+        ref = g[f"ious_{G}"]
+        np.testing.assert_allclose(got, ref, atol=2e-6)
+        assert (np.argmax(got, 0) == np.argmax(ref, 0)).all()
+        assert ((got > np.float32(0.7)) == (ref > np.float32(0.7))).all()
+        np.testing.assert_allclose(aa.cpu().numpy(), g[f"anchors_{G}"][:, 0] * g[f"anchors_{G}"][:, 1])
+
+
+def test_small_helpers(golden):
+    from cy4 import geometry as cg
+    from oracle import geometry as og
+    g = golden("rgiou_pairs.npz")
+    pred, tgt = g["pred"][:50], g["tgt"][:50]
+    yaw_p = np.arctan2(pred[:, 4], pred[:, 5]).astype(np.float32)
+    c = cg.get_corners_vectorize(*(torch.tensor(v, device="cuda") for v in (pred[:, 0], pred[:, 1], pred[:, 2], pred[:, 3], yaw_p)))
+    assert c.shape == (50, 4, 2)
+    oc = np.stack([og.corners(*pred[k, :4], yaw_p[k]) for k in range(50)])
+    np.testing.assert_allclose(c.cpu().numpy(), oc, atol=2e-5)
+    yaw_t = np.arctan2(tgt[:, 4], tgt[:, 5]).astype(np.float32)
+    tc = np.stack([og.corners(*tgt[k, :4], yaw_t[k]) for k in range(50)])
+    ia = cg.intersection_area(torch.tensor(oc, device="cuda"), torch.tensor(tc, device="cuda")).cpu().numpy()
+    oa = np.array([og.intersection_area(oc[k], tc[k]) for k in range(50)], np.float32)
+    np.testing.assert_allclose(ia, oa, atol=1e-6, rtol=1e-6)
+    one = cg.intersection_area(torch.tensor(oc[0]), torch.tensor(tc[0]))      # CPU tensors in, CPU tensor out
+    assert one.device.type == "cpu" and abs(float(one) - oa[0]) < 1e-6
+    pa = cg.PolyArea2D(torch.tensor(oc[3], device="cuda"))
+    assert abs(float(pa) - og.poly_area(oc[3])) < 1e-6
