@@ -1,0 +1,288 @@
+// conv_api.cu -- C-ABI of the convolution stack: fprop / dgrad launch set-up (tensor maps, tap
+// tables, tile shapes), weight packing, stem im2col.  Kernels live in conv_tc.cu / conv_wgrad.cu.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace cy4 {
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static int pick_block_n(int cout_pad)
+{
+    for (int bn : {256, 128, 64, 32})
+        if (cout_pad % bn == 0) return bn;
+    return 32;
+}
+
+// Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
+struct GenericConv {
+    const void *a; int B, Ha, Wa, Ca; int64_t lda;
+    int lower_w, lower_h, upper_w, upper_h, tstride;   // im2col box
+    int Po, Qo;                                        // base-pixel grid per image
+    int ntaps; uint8_t ow[kMaxTaps], oh[kMaxTaps]; int kofs[kMaxTaps];
+    const void *w; int w_rows_pad; int64_t w_ktot;     // packed weights [rows_pad][ktot]
+    int N;                                             // real output channels
+    void *y; int64_t ldy; uint32_t flags;
+    int omap, OH, OW, ostep, oh0, ow0;
+    const float *bias; float *ch_sum, *ch_sqsum;
+    int a_matrix;
+};
+
+static int run_generic(const GenericConv &g, cudaStream_t st)
+{
+    ConvKParams p;
+    memset(&p, 0, sizeof(p));
+    p.kchunk = (g.Ca % 64 == 0) ? 64 : 32;
+    if (g.Ca % 32 != 0) { set_error("conv: input channels (%d) must be a multiple of 32", g.Ca); return -1; }
+    p.cin_chunks = g.Ca / p.kchunk;
+    p.M = g.B * g.Po * g.Qo;
+    p.N = g.N;
+    p.block_n = pick_block_n(g.w_rows_pad);
+    p.tiles_m = (p.M + 127) / 128;
+    p.tiles_n = g.w_rows_pad / p.block_n;
+    p.ntaps = g.ntaps;
+    p.a_mode = g.a_matrix ? 0 : 1;
+    p.ab_fmt = 0;
+    p.Po = g.Po; p.Qo = g.Qo; p.tstride = g.tstride; p.lower_w = g.lower_w; p.lower_h = g.lower_h;
+    for (int t = 0; t < g.ntaps; ++t) { p.tap_ow[t] = g.ow[t]; p.tap_oh[t] = g.oh[t]; p.tap_kofs[t] = g.kofs[t]; }
+    p.y = g.y; p.ldy = g.ldy; p.flags = g.flags;
+    p.omap = g.omap; p.OH = g.OH; p.OW = g.OW; p.ostep = g.ostep; p.oh0 = g.oh0; p.ow0 = g.ow0;
+    p.bias = g.bias; p.ch_sum = g.ch_sum; p.ch_sqsum = g.ch_sqsum;
+    if (p.M <= 0) return 0;
+    const int swz = p.kchunk * 2;
+    alignas(64) CUtensorMap tmA, tmB;
+    int rc;
+    if (g.a_matrix)
+        rc = make_tmap_2d(&tmA, g.a, (uint64_t)g.Ca, (uint64_t)p.M, (uint64_t)g.lda * 2, p.kchunk, 128, swz, 0);
+    else
+        rc = make_tmap_im2col(&tmA, g.a, g.Ca, g.Wa, g.Ha, g.B, g.lda, g.lower_w, g.lower_h, g.upper_w, g.upper_h, p.kchunk,
+                              128, g.tstride, swz, 0);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n, swz, 0);
+    if (rc) return rc;
+    return launch_conv_tc(tmA, tmB, p, st);
+}
+
+static int check_conv_desc(const cy4_conv_desc *d, const char *who)
+{
+    if (!d || d->B <= 0 || d->Hi <= 0 || d->Wi <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->ksize <= 0 || d->ksize > 3 ||
+        d->stride <= 0 || d->stride > 2 || d->pad < 0) {
+        set_error("%s: bad conv descriptor", who);
+        return -1;
+    }
+    const int ho = (d->Hi + 2 * d->pad - d->ksize) / d->stride + 1, wo = (d->Wi + 2 * d->pad - d->ksize) / d->stride + 1;
+    if (ho != d->Ho || wo != d->Wo) { set_error("%s: Ho/Wo (%d,%d) inconsistent with the conv geometry (%d,%d)", who, d->Ho, d->Wo, ho, wo); return -1; }
+    if ((d->ldx % 8) || d->ldx < d->Cin) { set_error("%s: ldx must be a multiple of 8 and >= Cin", who); return -1; }
+    return 0;
+}
+
+// ---- packing kernels -----------------------------------------------------------------------------
+__global__ void pack_fprop_kernel(const float *__restrict__ w, int Cout, int Cin, int k, int cin_pad, int cout_pad, __half *__restrict__ out)
+{
+    // out[co][r][s][ci]  (ci < cin_pad), zero padded
+    const int64_t total = (int64_t)cout_pad * k * k * cin_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_pad);
+        int64_t r = i / cin_pad;
+        const int s = (int)(r % k); r /= k;
+        const int rr = (int)(r % k);
+        const int co = (int)(r / k);
+        float v = 0.f;
+        if (co < Cout && ci < Cin) v = w[(((int64_t)co * Cin + ci) * k + rr) * k + s];
+        out[i] = __float2half_rn(v);
+    }
+}
+
+__global__ void pack_dgrad_kernel(const float *__restrict__ w, int Cout, int Cin, int k, int cin_rows_pad, __half *__restrict__ out)
+{
+    // out[ci][r][s][co]
+    const int64_t total = (int64_t)cin_rows_pad * k * k * Cout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        int64_t r = i / Cout;
+        const int s = (int)(r % k); r /= k;
+        const int rr = (int)(r % k);
+        const int ci = (int)(r / k);
+        float v = 0.f;
+        if (ci < Cin) v = w[(((int64_t)co * Cin + ci) * k + rr) * k + s];
+        out[i] = __float2half_rn(v);
+    }
+}
+
+__global__ void unpack_wgrad_kernel(const float *__restrict__ acc, int Cout, int Cin, int k, int cin_pad, float scale, int accumulate,
+                                    float *__restrict__ gw)
+{
+    // gw[co][ci][r][s] (+)= scale * acc[co][r*k+s][ci]
+    const int64_t total = (int64_t)Cout * Cin * k * k;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(i % k);
+        int64_t r = i / k;
+        const int rr = (int)(r % k); r /= k;
+        const int ci = (int)(r % Cin);
+        const int co = (int)(r / Cin);
+        const float v = scale * acc[((int64_t)co * k * k + rr * k + s) * cin_pad + ci];
+        gw[i] = accumulate ? gw[i] + v : v;
+    }
+}
+
+__global__ void stem_im2col_kernel(const float *__restrict__ x, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+                                   __half *__restrict__ cols)
+{
+    // one thread per output pixel: 32 halves (64 B) per row, (r, s, c) order then zeros
+    const int64_t M = (int64_t)B * Ho * Wo;
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int q = (int)(m % Wo);
+    const int pp = (int)((m / Wo) % Ho);
+    const int b = (int)(m / ((int64_t)Wo * Ho));
+    __align__(16) __half row[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) row[i] = __float2half_rn(0.f);
+    int idx = 0;
+    for (int r = 0; r < k; ++r)
+        for (int s = 0; s < k; ++s) {
+            const int h = pp * stride - pad + r, w = q * stride - pad + s;
+            const bool in = h >= 0 && h < H && w >= 0 && w < W;
+            for (int c = 0; c < C; ++c, ++idx)
+                if (idx < 32 && in) row[idx] = __float2half_rn(__ldg(x + (((int64_t)b * C + c) * H + h) * W + w));
+        }
+    uint4 *dst = (uint4 *)(cols + m * 32);
+    const uint4 *src = (const uint4 *)row;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = src[i];
+}
+
+}  // namespace cy4
+
+using namespace cy4;
+
+extern "C" {
+
+int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias, float *ch_sum,
+                 float *ch_sqsum, void *stream)
+{
+    if (check_conv_desc(d, "cy4_conv_fwd")) return -1;
+    CY4_CHECK_ARG(x && w_fprop && y, "cy4_conv_fwd: null pointer");
+    CY4_CHECK_ARG(!(d->flags & CY4_CONV_STATS) || (ch_sum && ch_sqsum), "cy4_conv_fwd: STATS needs ch_sum / ch_sqsum");
+    const int cout_pad = round_up(d->Cout, 32);
+    CY4_CHECK_ARG(d->ldy >= cout_pad, "cy4_conv_fwd: ldy must be >= Cout rounded up to 32");
+    CY4_CHECK_ARG((d->flags & CY4_CONV_OUT_F32) ? (d->ldy % 4 == 0) : (d->ldy % 8 == 0), "cy4_conv_fwd: ldy alignment");
+    GenericConv g;
+    memset(&g, 0, sizeof(g));
+    const int k = d->ksize;
+    g.a = x; g.B = d->B; g.Ha = d->Hi; g.Wa = d->Wi; g.Ca = d->Cin; g.lda = d->ldx;
+    g.lower_w = g.lower_h = -d->pad;
+    g.upper_w = g.upper_h = d->pad - (k - 1);
+    g.tstride = d->stride;
+    g.Po = d->Ho; g.Qo = d->Wo;
+    g.ntaps = k * k;
+    for (int r = 0; r < k; ++r)
+        for (int s = 0; s < k; ++s) { g.ow[r * k + s] = (uint8_t)s; g.oh[r * k + s] = (uint8_t)r; g.kofs[r * k + s] = (r * k + s) * d->Cin; }
+    g.w = w_fprop; g.w_rows_pad = cout_pad; g.w_ktot = (int64_t)k * k * d->Cin;
+    g.N = d->Cout;
+    g.y = y; g.ldy = d->ldy;
+    g.flags = ((d->flags & CY4_CONV_OUT_F32) ? CONV_F_OUT_F32 : 0) | ((d->flags & CY4_CONV_STATS) ? CONV_F_STATS : 0) |
+              ((d->flags & CY4_CONV_ACCUM) ? CONV_F_ACCUM : 0);
+    g.bias = bias; g.ch_sum = ch_sum; g.ch_sqsum = ch_sqsum;
+    g.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
+    if (g.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_fwd: matrix mode needs a 1x1/s1/p0 conv");
+    return run_generic(g, (cudaStream_t)stream);
+}
+
+int cy4_conv_dgrad(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, void *stream)
+{
+    if (check_conv_desc(d, "cy4_conv_dgrad")) return -1;
+    CY4_CHECK_ARG(dy && w_dgrad && dx, "cy4_conv_dgrad: null pointer");
+    CY4_CHECK_ARG(d->Cout % 32 == 0, "cy4_conv_dgrad: Cout must be a multiple of 32 (pad dy)");
+    CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx % 8 == 0 && d->ldy % 8 == 0, "cy4_conv_dgrad: channel alignment");
+    const int k = d->ksize;
+    GenericConv g;
+    memset(&g, 0, sizeof(g));
+    g.a = dy; g.B = d->B; g.Ha = d->Ho; g.Wa = d->Wo; g.Ca = d->Cout; g.lda = d->ldy;
+    g.w = w_dgrad; g.w_rows_pad = round_up(d->Cin, 32); g.w_ktot = (int64_t)k * k * d->Cout;
+    g.N = d->Cin;
+    g.y = dx; g.ldy = d->ldx;
+    g.flags = (d->flags & CY4_CONV_ACCUM) ? CONV_F_ACCUM : 0;
+    if (d->stride == 1) {
+        CY4_CHECK_ARG(d->pad == k / 2 && (k & 1), "cy4_conv_dgrad: stride 1 needs odd k and pad = k/2");
+        // dx[h] = sum_r dy[h + pad - r] w[r]: base = h + lower, offset o = k-1-r
+        g.lower_w = g.lower_h = d->pad - (k - 1);
+        g.upper_w = g.upper_h = g.lower_w;               // Ho == Hi: the box spans Hi base pixels
+        g.tstride = 1;
+        g.Po = d->Hi; g.Qo = d->Wi;
+        g.ntaps = k * k;
+        for (int o_r = 0; o_r < k; ++o_r)
+            for (int o_s = 0; o_s < k; ++o_s) {
+                const int t = o_r * k + o_s;
+                g.ow[t] = (uint8_t)o_s; g.oh[t] = (uint8_t)o_r;
+                g.kofs[t] = ((k - 1 - o_r) * k + (k - 1 - o_s)) * d->Cout;
+            }
+        return run_generic(g, (cudaStream_t)stream);
+    }
+    CY4_CHECK_ARG(d->stride == 2 && k == 3 && d->pad == 1 && (d->Hi % 2 == 0) && (d->Wi % 2 == 0),
+                  "cy4_conv_dgrad: stride 2 is implemented for k=3, pad=1, even input size");
+    // hi = 2*ho - 1 + r.  Parity class ph: ph=0 -> (r=1, o=0);  ph=1 -> (r=0, o=1), (r=2, o=0), where o = ho - i.
+    g.lower_w = g.lower_h = 0; g.upper_w = g.upper_h = 0; g.tstride = 1;
+    g.Po = d->Hi / 2; g.Qo = d->Wi / 2;
+    g.omap = 1; g.OH = d->Hi; g.OW = d->Wi; g.ostep = 2;
+    static const int cls_n[2] = {1, 2};
+    static const int cls_r[2][2] = {{1, 0}, {0, 2}};
+    static const int cls_o[2][2] = {{0, 0}, {1, 0}};
+    for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+            g.oh0 = ph; g.ow0 = pw;
+            g.ntaps = 0;
+            for (int a = 0; a < cls_n[ph]; ++a)
+                for (int b = 0; b < cls_n[pw]; ++b) {
+                    const int t = g.ntaps++;
+                    g.oh[t] = (uint8_t)cls_o[ph][a]; g.ow[t] = (uint8_t)cls_o[pw][b];
+                    g.kofs[t] = (cls_r[ph][a] * 3 + cls_r[pw][b]) * d->Cout;
+                }
+            const int rc = run_generic(g, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    return 0;
+}
+
+int cy4_pack_weight_fprop(const float *w_oihw, int Cout, int Cin, int ksize, int cin_pad, void *w_packed, void *stream)
+{
+    CY4_CHECK_ARG(w_oihw && w_packed && Cout > 0 && Cin > 0 && ksize > 0 && cin_pad >= Cin, "cy4_pack_weight_fprop: bad argument");
+    const int cout_pad = round_up(Cout, 32);
+    const int64_t total = (int64_t)cout_pad * ksize * ksize * cin_pad;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    pack_fprop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, ksize, cin_pad, cout_pad, (__half *)w_packed);
+    return cy4_launch_status("cy4_pack_weight_fprop");
+}
+
+int cy4_pack_weight_dgrad(const float *w_oihw, int Cout, int Cin, int ksize, void *w_packed, void *stream)
+{
+    CY4_CHECK_ARG(w_oihw && w_packed && Cout > 0 && Cin > 0 && ksize > 0, "cy4_pack_weight_dgrad: bad argument");
+    const int rows = round_up(Cin, 32);
+    const int64_t total = (int64_t)rows * ksize * ksize * Cout;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    pack_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, ksize, rows, (__half *)w_packed);
+    return cy4_launch_status("cy4_pack_weight_dgrad");
+}
+
+int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_pad, float scale, int accumulate, float *gw_oihw,
+                     void *stream)
+{
+    CY4_CHECK_ARG(dw_acc && gw_oihw && Cout > 0 && Cin > 0 && ksize > 0 && cin_pad >= Cin, "cy4_unpack_wgrad: bad argument");
+    const int64_t total = (int64_t)Cout * Cin * ksize * ksize;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    unpack_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dw_acc, Cout, Cin, ksize, cin_pad, scale, accumulate, gw_oihw);
+    return cy4_launch_status("cy4_unpack_wgrad");
+}
+
+int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int ksize, int stride, int pad, void *cols, void *stream)
+{
+    CY4_CHECK_ARG(x_nchw && cols && B > 0 && C > 0 && C * ksize * ksize <= 32, "cy4_stem_im2col: needs C*k*k <= 32");
+    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+    const int64_t M = (int64_t)B * Ho * Wo;
+    stem_im2col_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x_nchw, B, C, H, W, ksize, stride, pad, Ho, Wo, (__half *)cols);
+    return cy4_launch_status("cy4_stem_im2col");
+}
+
+}  // extern "C"

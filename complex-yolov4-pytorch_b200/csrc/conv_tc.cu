@@ -1,0 +1,317 @@
+// conv_tc.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+//   D[m, n] = sum_{tap, c} X[pixel(m) + tap, c] * W[n, tap, c]       m = output pixel, n = out channel
+//
+// One persistent CTA per SM, 6 warps, three roles:
+//   warp 0      TMA producer   im2col-mode TMA gathers a 128-pixel x kchunk-channel slab of the NHWC
+//                              activation per (tap, channel chunk) -- padding / stride / image borders
+//                              are resolved by the TMA unit (OOB zero fill); a tiled TMA brings the
+//                              matching [block_n x kchunk] slab of the K-major packed weights.
+//   warp 1      MMA issuer     one lane issues tcgen05.mma (M=128, N=block_n, K=16) on the 128B/64B
+//                              swizzled smem slabs; fp32 accumulators live in TMEM, double buffered
+//                              (2 x block_n columns) so the epilogue of tile i overlaps tile i+1.
+//   warps 2..5  epilogue       tcgen05.ld the accumulator rows, fused per-channel sum / sum^2 for the
+//                              training-mode BatchNorm that follows (warp reduce-scatter + one atomic
+//                              per channel per warp), bias / fp16 or fp32 conversion, store.
+// The same kernel serves fprop, stride-1 dgrad (flipped/transposed weights) and the four parity
+// classes of stride-2 dgrad (generic tap table + strided output-row mapping).
+// Reference ops replaced: nn.Conv2d inside src/models/darknet2pytorch.py:247-278 (cuDNN via ATen).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+#include "conv_tc.cuh"
+
+namespace cy4 {
+using namespace sm100;
+
+constexpr int kBlockM = 128;
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kAStageBytes = kBlockM * 128;        // 16 KB (kchunk 64) ; 8 KB used when kchunk 32
+constexpr int kBStageBytes = 256 * 128;            // 32 KB (block_n 256, kchunk 64)
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = 512;
+
+struct SmemCtl {
+    uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvKParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + kStages * kAStageBytes;
+    SmemCtl *ctl = (SmemCtl *)(smem + kStages * (kAStageBytes + kBStageBytes));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_total = p.tiles_m * p.tiles_n;
+    const int num_kb = p.ntaps * p.cin_chunks;
+    const uint32_t a_bytes = kBlockM * p.kchunk * 2, b_bytes = p.block_n * p.kchunk * 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(&ctl->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+                const int n_blk = t % p.tiles_n, m_blk = t / p.tiles_n;
+                const int m0 = m_blk * kBlockM;
+                // base pixel of the tile in the im2col "base pixel" space
+                const int img = m0 / (p.Po * p.Qo);
+                const int rem = m0 - img * (p.Po * p.Qo);
+                const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
+                const int bw = qi * p.tstride + p.lower_w, bh = pi * p.tstride + p.lower_h;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                        mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
+                        if (p.a_mode == 1)
+                            tma_load_im2col_4d(&tmA, &ctl->full[stage], sA + stage * kAStageBytes, cc * p.kchunk, bw, bh, img,
+                                               (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
+                        else
+                            tma_load_2d(&tmA, &ctl->full[stage], sA + stage * kAStageBytes, cc * p.kchunk, m0);
+                        tma_load_2d(&tmB, &ctl->full[stage], sB + stage * kBStageBytes, p.tap_kofs[tap] + cc * p.kchunk,
+                                    n_blk * p.block_n);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n, p.ab_fmt, 0, 0);
+        const uint32_t sw = p.kchunk == 64 ? SW_128B : SW_64B;
+        const uint32_t sbo = p.kchunk == 64 ? 1024 : 512;
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+            mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * p.block_n;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&ctl->full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(sA + stage * kAStageBytes);
+                    const uint32_t b_addr = smem_u32(sB + stage * kBStageBytes);
+                    const int nk = p.kchunk / 16;
+                    for (int k = 0; k < nk; ++k) {
+                        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, sbo, sw);
+                        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, sbo, sw);
+                        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&ctl->empty[stage]);
+                    if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+            const int n_blk = t % p.tiles_n, m_blk = t / p.tiles_n;
+            const int m = m_blk * kBlockM + quarter * 32 + lane;          // this thread's GEMM row
+            const bool row_ok = m < p.M;
+            // output row address (dense, or a strided parity class of a larger image)
+            int64_t orow = m;
+            if (p.omap) {
+                const int img = m / (p.Po * p.Qo);
+                const int rem = m - img * (p.Po * p.Qo);
+                const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
+                orow = ((int64_t)img * p.OH + (pi * p.ostep + p.oh0)) * p.OW + (qi * p.ostep + p.ow0);
+            }
+            mbar_wait(&ctl->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * p.block_n;
+            for (int c = 0; c < p.block_n / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c * 32, v);
+                tmem_ld_wait();
+                const int n0 = n_blk * p.block_n + c * 32;
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (p.flags & CONV_F_OUT_F32) {
+                    if (row_ok) {
+                        float *dst = (float *)p.y + orow * p.ldy + n0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 o;
+                            o.x = f[i] + (p.bias ? __ldg(p.bias + n0 + i) : 0.f);
+                            o.y = f[i + 1] + (p.bias ? __ldg(p.bias + n0 + i + 1) : 0.f);
+                            o.z = f[i + 2] + (p.bias ? __ldg(p.bias + n0 + i + 2) : 0.f);
+                            o.w = f[i + 3] + (p.bias ? __ldg(p.bias + n0 + i + 3) : 0.f);
+                            *(float4 *)(dst + i) = o;
+                        }
+                    }
+                } else {
+                    if (row_ok) {
+                        __half *dst = (__half *)p.y + orow * p.ldy + n0;
+                        if (p.flags & CONV_F_ACCUM) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                uint4 old = *(const uint4 *)(dst + i);
+                                const __half2 *oh = (const __half2 *)&old;
+                                uint4 o; __half2 *ph = (__half2 *)&o;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 of = __half22float2(oh[j]);
+                                    ph[j] = __floats2half2_rn(f[i + 2 * j] + of.x, f[i + 2 * j + 1] + of.y);
+                                }
+                                *(uint4 *)(dst + i) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                uint4 o; __half2 *ph = (__half2 *)&o;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(f[i + 2 * j], f[i + 2 * j + 1]);
+                                *(uint4 *)(dst + i) = o;
+                            }
+                        }
+                    }
+                }
+                if (p.flags & CONV_F_STATS) {
+                    // Per-channel sum and sum of squares over this warp's 32 rows (rows >= M are exact
+                    // zeros: their im2col pixels are out of bounds).  Reduce-scatter: lane L ends up
+                    // with the totals of column L.
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { s1[i] = f[i]; s2[i] = f[i] * f[i]; }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool hi = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send1 = hi ? s1[i] : s1[i + off];
+                            const float send2 = hi ? s2[i] : s2[i + off];
+                            const float r1 = __shfl_xor_sync(0xffffffffu, send1, off);
+                            const float r2 = __shfl_xor_sync(0xffffffffu, send2, off);
+                            s1[i] = (hi ? s1[i + off] : s1[i]) + r1;
+                            s2[i] = (hi ? s2[i + off] : s2[i]) + r2;
+                        }
+                    }
+                    if (n0 + lane < p.N) {
+                        atomicAdd(p.ch_sum + n0 + lane, s1[0]);
+                        atomicAdd(p.ch_sqsum + n0 + lane, s2[0]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+}
+
+// --------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+static int g_driver_version = 0;
+
+static int load_driver_entry_points()
+{
+    if (g_encodeTiled && g_encodeIm2col) return 0;
+    cudaDriverEntryPointQueryResult qr;
+    void *fn = nullptr;
+    CY4_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available in this driver"); return -2; }
+    g_encodeTiled = (PFN_encodeTiled)fn;
+    fn = nullptr;
+    CY4_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeIm2col not available in this driver"); return -2; }
+    g_encodeIm2col = (PFN_encodeIm2col)fn;
+    cudaDriverGetVersion(&g_driver_version);
+    return 0;
+}
+
+int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes, int dtype_bf16)
+{
+    if (load_driver_entry_points()) return -2;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = g_encodeTiled(tm, dtype_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                               const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu stride %llu box %u x %u", (int)r,
+                                       (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner, box_outer); return -2; }
+    return 0;
+}
+
+// NHWC activation viewed as (C, W, H, N); ld = channel stride in elements.
+int make_tmap_im2col(CUtensorMap *tm, const void *base, int C, int W, int H, int N, int64_t ld, int lower_w, int lower_h,
+                     int upper_w, int upper_h, int chan_per_pixel, int pixels_per_col, int tstride, int swizzle_bytes,
+                     int dtype_bf16)
+{
+    if (load_driver_entry_points()) return -2;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * W, (cuuint64_t)ld * 2 * W * H};
+    int lower[2] = {lower_w, lower_h};
+    int upper[2] = {upper_w, upper_h};
+    cuuint32_t estr[4] = {1, (cuuint32_t)tstride, (cuuint32_t)tstride, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = g_encodeIm2col(tm, dtype_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                                const_cast<void *>(base), dims, strides, lower, upper, (cuuint32_t)chan_per_pixel,
+                                (cuuint32_t)pixels_per_col, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d): C %d W %d H %d N %d ld %lld lower %d,%d upper %d,%d cpp %d ppc %d",
+                                       (int)r, C, W, H, N, (long long)ld, lower_w, lower_h, upper_w, upper_h, chan_per_pixel, pixels_per_col); return -2; }
+    // Driver workaround carried by CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): for drivers
+    // <= 13.1 and tensors smaller than 128 KiB, bit 21 of the second descriptor word must be cleared.
+    if (g_driver_version <= 13010 && (uint64_t)ld * 2 * W * H * N < 131072)
+        reinterpret_cast<uint64_t *>(tm)[1] &= ~(1llu << 21);
+    return 0;
+}
+
+int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvKParams &p, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CY4_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = std::min(tiles, sm_count());
+    conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, p);
+    return cy4_launch_status("conv_tc_kernel");
+}
+
+}  // namespace cy4

@@ -1,0 +1,41 @@
+// conv_tc.cuh -- kernel parameter block and host helpers shared by the tensor-core conv kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cy4 {
+
+enum : uint32_t {
+    CONV_F_OUT_F32 = 1u,   // fp32 output (+ optional bias) instead of fp16
+    CONV_F_STATS = 2u,     // accumulate per-channel sum / sum^2 of the fp32 accumulators
+    CONV_F_ACCUM = 4u,     // y += result (fp16 read-modify-write), used by dgrad into shared grads
+};
+
+constexpr int kMaxTaps = 16;
+
+struct ConvKParams {
+    int M, N;                    // GEMM rows (output pixels of this launch), real output channels
+    int tiles_m, tiles_n, block_n;
+    int kchunk, cin_chunks, ntaps;
+    int a_mode;                  // 0: A is a plain [M, K] matrix (tiled TMA) ; 1: im2col TMA
+    int ab_fmt;                  // 0 fp16, 1 bf16
+    // im2col base-pixel space: pixel m -> (img, pi, qi) over Po x Qo ; TMA base = (qi*tstride + lower_w, ...)
+    int Po, Qo, tstride, lower_w, lower_h;
+    uint8_t tap_ow[kMaxTaps], tap_oh[kMaxTaps];
+    int tap_kofs[kMaxTaps];      // k offset of each tap inside a packed weight row
+    // output
+    void *y; int64_t ldy;
+    int omap, OH, OW, ostep, oh0, ow0;   // strided output-row mapping (stride-2 dgrad parity classes)
+    const float *bias; float *ch_sum, *ch_sqsum;
+    uint32_t flags;
+};
+
+int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes, int dtype_bf16);
+int make_tmap_im2col(CUtensorMap *tm, const void *base, int C, int W, int H, int N, int64_t ld, int lower_w, int lower_h,
+                     int upper_w, int upper_h, int chan_per_pixel, int pixels_per_col, int tstride, int swizzle_bytes,
+                     int dtype_bf16);
+int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvKParams &p, cudaStream_t st);
+
+}  // namespace cy4

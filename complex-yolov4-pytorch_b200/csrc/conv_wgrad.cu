@@ -1,0 +1,208 @@
+// conv_wgrad.cu -- weight gradient of the convolution on tcgen05:
+//
+//   dW[co, tap, ci] = sum_{pixels m} dY[m, co] * X[pixel(m) + tap, ci]
+//
+// a GEMM whose reduction dimension is the pixel index, so BOTH operands are "MN-major" in shared
+// memory (channels contiguous, pixels strided) -- the UMMA instruction descriptor's a_major/b_major
+// bits select that, and TMA delivers the slabs in exactly the canonical MN-major 128B-swizzle
+// layout: 64-pixel x 64-channel boxes, 8-pixel groups 1024 B apart (SBO), 64-channel column blocks
+// one box (8192 B) apart (LBO).  X goes through the same im2col-mode tensor map as fprop.
+//
+// Work item = (128 output channels) x (<= 256 input channels) x (one tap) x (one slice of the
+// pixel range); split-K slices add their fp32 partial tile into dw_acc with red.global.add.
+// Reference op replaced: the autograd backward of nn.Conv2d (weight), src/train.py:212.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+#include "conv_tc.cuh"
+
+namespace cy4 {
+using namespace sm100;
+
+constexpr int kWStages = 4;
+constexpr int kWThreads = 192;
+constexpr int kPixBlk = 64;                         // pixels (GEMM K) per pipeline stage
+constexpr int kWAStage = 2 * kPixBlk * 128;         // dY: two 64-channel boxes  = 16 KB
+constexpr int kWBStage = 4 * kPixBlk * 128;         // X : up to four boxes      = 32 KB
+constexpr int kWSmem = kWStages * (kWAStage + kWBStage) + 1024 + 256;
+
+struct WgradParams {
+    int Mpix;                    // total pixels (B*Ho*Wo)
+    int Cout, Cin;               // real sizes
+    int m_tiles, n_tiles, block_n, ntaps, ksplit, kblocks;   // kblocks = ceil(Mpix/64)
+    int b_boxes;                 // block_n / 64 (or 1 when the 64B-swizzle N=32 path is used)
+    int b_sw64;                  // 1: X has 32 channels, single [64 px x 32 ch] box, 64B swizzle
+    int a_matrix;                // 1: X is a plain matrix (tiled TMA), only with ntaps == 1
+    int Po, Qo, tstride, lower_w, lower_h;
+    uint8_t tap_ow[kMaxTaps], tap_oh[kMaxTaps];
+    float *dw; int64_t dw_row;   // dw_acc[co * dw_row + tap * cin_pad + ci]
+    int cin_pad;
+};
+
+struct WCtl {
+    uint64_t full[kWStages], empty[kWStages], tmem_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WgradParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + kWStages * kWAStage;
+    WCtl *ctl = (WCtl *)(smem + kWStages * (kWAStage + kWBStage));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // decode the work item
+    int item = blockIdx.x;
+    const int ks = item % p.ksplit; item /= p.ksplit;
+    const int tap = item % p.ntaps; item /= p.ntaps;
+    const int n_blk = item % p.n_tiles;
+    const int m_blk = item / p.n_tiles;
+    const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+    const int kb0 = ks * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
+    const int nkb = kb1 - kb0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDy); prefetch_tmap(&tmX);
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+        mbar_init(&ctl->tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<256>(&ctl->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (nkb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const int a_boxes = (m_blk * 128 + 64 < p.Cout) ? 2 : 1;       // skip a fully out-of-range box
+                const uint32_t bytes = a_boxes * kPixBlk * 128 + (p.b_sw64 ? kPixBlk * 64 : p.b_boxes * kPixBlk * 128);
+                int stage = 0; uint32_t phase = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int m0 = kb * kPixBlk;
+                    mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    mbar_expect_tx(&ctl->full[stage], bytes);
+                    for (int bx = 0; bx < a_boxes; ++bx)
+                        tma_load_2d(&tmDy, &ctl->full[stage], sA + stage * kWAStage + bx * (kPixBlk * 128), m_blk * 128 + bx * 64, m0);
+                    if (p.a_matrix) {
+                        for (int bx = 0; bx < p.b_boxes; ++bx)
+                            tma_load_2d(&tmX, &ctl->full[stage], sB + stage * kWBStage + bx * (kPixBlk * 128),
+                                        n_blk * p.block_n + bx * 64, m0);
+                    } else {
+                        const int img = m0 / (p.Po * p.Qo);
+                        const int rem = m0 - img * (p.Po * p.Qo);
+                        const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
+                        const int bw = qi * p.tstride + p.lower_w, bh = pi * p.tstride + p.lower_h;
+                        for (int bx = 0; bx < p.b_boxes; ++bx)
+                            tma_load_im2col_4d(&tmX, &ctl->full[stage], sB + stage * kWBStage + bx * (kPixBlk * 128),
+                                               n_blk * p.block_n + bx * 64, bw, bh, img, (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
+                    }
+                    if (++stage == kWStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            const uint32_t idesc = make_idesc_f16(128, p.block_n, 0, 1, 1);       // both operands MN-major
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&ctl->full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(sA + stage * kWAStage);
+                    const uint32_t b_addr = smem_u32(sB + stage * kWBStage);
+#pragma unroll
+                    for (int k = 0; k < kPixBlk / 16; ++k) {
+                        // 16 pixels = two 8-row groups: advance 16 rows of 128 B (64 B in the 64B-swizzle case)
+                        const uint64_t ad = make_smem_desc(a_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
+                        const uint64_t bd = p.b_sw64 ? make_smem_desc(b_addr + k * 16 * 64, 0, 512, SW_64B)
+                                                     : make_smem_desc(b_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
+                        umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&ctl->empty[stage]);
+                    if (kb == nkb - 1) umma_commit(&ctl->tmem_full);
+                }
+                __syncwarp();
+                if (++stage == kWStages) { stage = 0; phase ^= 1; }
+            }
+        } else {
+            const int quarter = warp & 3;
+            const int co = m_blk * 128 + quarter * 32 + lane;
+            mbar_wait(&ctl->tmem_full, 0);
+            tc_fence_after();
+            float *row = p.dw + (int64_t)co * p.dw_row + (int64_t)tap * p.cin_pad;
+            for (int c = 0; c < p.block_n / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
+                const int ci0 = n_blk * p.block_n + c * 32;
+                if (co < p.Cout) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ci0 + i < p.Cin) atomicAdd(row + ci0 + i, __uint_as_float(v[i]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
+}
+
+}  // namespace cy4
+
+using namespace cy4;
+
+extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void *dy, float *dw_acc, void *stream)
+{
+    CY4_CHECK_ARG(d && x && dy && dw_acc, "cy4_conv_wgrad: null pointer");
+    CY4_CHECK_ARG(d->ksize >= 1 && d->ksize <= 3 && d->stride >= 1 && d->stride <= 2, "cy4_conv_wgrad: bad geometry");
+    const int k = d->ksize;
+    const int cout64 = (d->Cout + 63) / 64 * 64;
+    CY4_CHECK_ARG(d->ldy >= cout64 && d->ldy % 8 == 0, "cy4_conv_wgrad: dy must be allocated with ld >= Cout rounded up to 64");
+    const bool sw64 = d->Cin == 32 && d->ldx < 64;
+    const int cin64 = sw64 ? 32 : (d->Cin + 63) / 64 * 64;
+    CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx >= cin64 && d->ldx % 8 == 0, "cy4_conv_wgrad: x must be allocated with ld >= Cin rounded up to 64 (or Cin == 32)");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.Mpix = d->B * d->Ho * d->Wo;
+    p.Cout = d->Cout; p.Cin = d->Cin;
+    p.m_tiles = (d->Cout + 127) / 128;
+    p.block_n = sw64 ? 32 : std::min(cin64, 256);
+    p.n_tiles = (cin64 + p.block_n - 1) / p.block_n;
+    p.b_boxes = sw64 ? 1 : p.block_n / 64;
+    p.b_sw64 = sw64 ? 1 : 0;
+    p.ntaps = k * k;
+    p.kblocks = (p.Mpix + kPixBlk - 1) / kPixBlk;
+    const int items = p.m_tiles * p.n_tiles * p.ntaps;
+    p.ksplit = std::max(1, std::min(p.kblocks, (3 * sm_count() + items - 1) / items));
+    p.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
+    if (p.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_wgrad: matrix mode needs a 1x1/s1/p0 conv");
+    p.Po = d->Ho; p.Qo = d->Wo; p.tstride = d->stride; p.lower_w = p.lower_h = -d->pad;
+    for (int r = 0; r < k; ++r)
+        for (int s = 0; s < k; ++s) { p.tap_ow[r * k + s] = (uint8_t)s; p.tap_oh[r * k + s] = (uint8_t)r; }
+    p.cin_pad = d->Cin;
+    p.dw = dw_acc; p.dw_row = (int64_t)k * k * d->Cin;
+    if (p.Mpix <= 0) return 0;
+
+    alignas(64) CUtensorMap tmDy, tmX;
+    int rc = make_tmap_2d(&tmDy, dy, (uint64_t)cout64, (uint64_t)p.Mpix, (uint64_t)d->ldy * 2, 64, kPixBlk, 128, 0);
+    if (rc) return rc;
+    if (p.a_matrix)
+        rc = make_tmap_2d(&tmX, x, (uint64_t)cin64, (uint64_t)p.Mpix, (uint64_t)d->ldx * 2, sw64 ? 32 : 64, kPixBlk, sw64 ? 64 : 128, 0);
+    else
+        rc = make_tmap_im2col(&tmX, x, cin64, d->Wi, d->Hi, d->B, d->ldx, -d->pad, -d->pad, d->pad - (k - 1), d->pad - (k - 1),
+                              sw64 ? 32 : 64, kPixBlk, d->stride, sw64 ? 64 : 128, 0);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CY4_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
+        attr_set = true;
+    }
+    const int grid = items * p.ksplit;
+    conv_wgrad_kernel<<<grid, kWThreads, kWSmem, (cudaStream_t)stream>>>(tmDy, tmX, p);
+    return cy4_launch_status("cy4_conv_wgrad");
+}

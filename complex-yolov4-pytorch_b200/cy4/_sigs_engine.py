@@ -1,2 +1,33 @@
-"""ctypes signatures of the conv-engine entry points (filled in as csrc/ grows)."""
-SIGS = {}
+"""ctypes signatures of the conv-engine entry points (include/cy4.h, "convolution stack")."""
+import ctypes
+
+c_f = ctypes.c_void_p
+c_vp = ctypes.c_void_p
+c_i = ctypes.c_int
+c_i64 = ctypes.c_int64
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int32), ("Hi", ctypes.c_int32), ("Wi", ctypes.c_int32), ("Cin", ctypes.c_int32),
+                ("Ho", ctypes.c_int32), ("Wo", ctypes.c_int32), ("Cout", ctypes.c_int32),
+                ("ksize", ctypes.c_int32), ("stride", ctypes.c_int32), ("pad", ctypes.c_int32),
+                ("ldx", ctypes.c_int64), ("ldy", ctypes.c_int64),
+                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+PD = ctypes.POINTER(ConvDesc)
+
+SIGS = {
+    "cy4_conv_fwd": (c_i, [PD, c_f, c_f, c_f, c_f, c_f, c_f, c_vp]),
+    "cy4_conv_dgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
+    "cy4_conv_wgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
+    "cy4_pack_weight_fprop": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_vp]),
+    "cy4_pack_weight_dgrad": (c_i, [c_f, c_i, c_i, c_i, c_f, c_vp]),
+    "cy4_unpack_wgrad": (c_i, [c_f, c_i, c_i, c_i, c_i, ctypes.c_float, c_i, c_f, c_vp]),
+    "cy4_stem_im2col": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_vp]),
+}
+
+CONV_OUT_F32 = 1
+CONV_STATS = 2
+CONV_ACCUM = 4
+CONV_A_MATRIX = 8

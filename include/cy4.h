@@ -114,6 +114,51 @@ CY4_API int cy4_build_targets(const cy4_yolo_desc *d, const float *pred_boxes, c
                       float *tre, float *tcls, float *tconf, int64_t *idx, int32_t *status,
                       void *workspace, void *stream);
 
+
+/* ---- convolution stack on the tensor cores (tcgen05) -----------------------------------------
+ * Replaces nn.Conv2d inside models/darknet2pytorch.py:247-278 (create_network's conv blocks) and
+ * its autograd backward.  Activations are NHWC fp16 (channel stride ld, so producers can write
+ * into channel slices of a route/concat buffer); weights are K-major packed fp16:
+ *   fprop  [Cout_pad][kh][kw][Cin]   (cy4_pack_weight_fprop, from the module's OIHW fp32 parameter)
+ *   dgrad  [Cin_pad][kh][kw][Cout]   (cy4_pack_weight_dgrad)
+ * with *_pad = channels rounded up to a multiple of 32 (zero rows).  Cin must be a multiple of 32
+ * (the 3-channel stem goes through cy4_stem_im2col first, see below). */
+typedef struct cy4_conv_desc {
+    int32_t B, Hi, Wi, Cin;   /* input  [B,Hi,Wi,Cin], channel stride ldx (elements) */
+    int32_t Ho, Wo, Cout;     /* output [B,Ho,Wo,Cout], channel stride ldy (elements) */
+    int32_t ksize, stride, pad;
+    int64_t ldx, ldy;
+    uint32_t flags;           /* CY4_CONV_* */
+    uint32_t reserved;
+} cy4_conv_desc;
+
+#define CY4_CONV_OUT_F32 1u   /* y is fp32 (+ bias when bias != NULL); default fp16 */
+#define CY4_CONV_STATS   2u   /* also accumulate per-channel sum / sum of squares of the fp32 results
+                                 into ch_sum / ch_sqsum (atomicAdd; caller zeroes them) -- the batch
+                                 statistics of the BatchNorm2d that follows (darknet2pytorch.py:260) */
+#define CY4_CONV_A_MATRIX 8u  /* x is a plain [B*Ho*Wo, Cin] matrix (1x1/s1/p0 only): tiled TMA instead of
+                                 im2col TMA -- used for the stem's explicit im2col matrix */
+#define CY4_CONV_ACCUM   4u   /* y += result instead of y = result (fp16), for gradients of tensors
+                                 with several consumers (route / shortcut, darknet2pytorch.py:180-219) */
+
+/* y = conv(x, w) */
+CY4_API int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias,
+                         float *ch_sum, float *ch_sqsum, void *stream);
+/* dx (+)= conv_transpose(dy, w); d describes the FORWARD conv; dy [B,Ho,Wo,Cout] (ld = ldy),
+ * dx [B,Hi,Wi,Cin] (ld = ldx).  stride 1 (any odd k, pad = k/2) and stride 2 (k=3, pad=1, even Hi/Wi). */
+CY4_API int cy4_conv_dgrad(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, void *stream);
+/* dw_acc[Cout_pad][kh*kw][Cin] (fp32, caller-zeroed) += dy^T * im2col(x): split-K partial sums are
+ * added with atomics.  cy4_unpack_wgrad then writes the OIHW fp32 gradient of the parameter. */
+CY4_API int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void *dy, float *dw_acc, void *stream);
+
+CY4_API int cy4_pack_weight_fprop(const float *w_oihw, int Cout, int Cin, int ksize, int cin_pad, void *w_packed, void *stream);
+CY4_API int cy4_pack_weight_dgrad(const float *w_oihw, int Cout, int Cin, int ksize, void *w_packed, void *stream);
+CY4_API int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_pad, float scale, int accumulate,
+                             float *gw_oihw, void *stream);
+/* Stem: x NCHW fp32 [B,3,H,W] -> im2col matrix [B*Ho*Wo, 32] fp16 (27 taps*channels (r,s,c order) + 5 zeros) */
+CY4_API int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int ksize, int stride, int pad,
+                            void *cols /* [B*Ho*Wo, 32] fp16 */, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,186 @@
+"""GPU: tcgen05 implicit-GEMM convolution (fprop, dgrad) through the C-ABI against a plain PyTorch
+fp32 reference of the same op on the CPU (torch.nn.functional.conv2d), which is what the
+reference's nn.Conv2d (src/models/darknet2pytorch.py:258-264) computes.
+
+Tolerance: inputs are rounded to fp16 before BOTH implementations, so the only differences are the
+fp32 accumulation order and the fp16 rounding of the stored output: |err| <= 2e-3 * max|y| is far
+above that and far below any indexing / layout mistake (which gives O(1) errors)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+FWD_CASES = [
+    # B, H, W, Cin, Cout, k, stride
+    (2, 19, 19, 64, 64, 1, 1),      # 1x1, one k-block
+    (2, 19, 19, 128, 256, 1, 1),    # 1x1, block_n 256
+    (1, 38, 38, 64, 128, 3, 1),     # 3x3 pad 1 (im2col halo, image borders)
+    (3, 19, 19, 256, 512, 3, 1),    # M=1083 (tail tile), two n tiles
+    (2, 38, 38, 64, 128, 3, 2),     # stride 2
+    (2, 40, 24, 32, 64, 3, 1),      # Cin=32: 64B swizzle path, non-square
+    (2, 40, 24, 32, 64, 3, 2),
+    (2, 19, 19, 128, 30, 1, 1),     # head: Cout=30 padded to 32
+    (1, 76, 76, 128, 128, 3, 1),    # many tiles per CTA? (46 tiles) exercises pipeline wrap
+    (4, 76, 76, 64, 64, 1, 1),      # 181 tiles > 148 SMs: persistent loop + TMEM double buffer
+]
+
+
+def _ref_conv(x_nhwc16, w16, stride, pad):
+    x = x_nhwc16.float().permute(0, 3, 1, 2).cpu()
+    return F.conv2d(x, w16.float().cpu(), None, stride, pad).permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", FWD_CASES)
+def test_conv_fwd(B, H, W, Cin, Cout, k, stride):
+    from cy4 import convops as co
+    torch.manual_seed(B * 1000 + H + Cin + Cout + k)
+    pad = (k - 1) // 2
+    x = torch.randn(B, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).half()
+    wp = co.pack_fprop(w.float())
+    y = co.conv_fwd(x, wp, Cout, k, stride, pad)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, stride, pad)
+    got = y[..., :Cout].float().cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, err
+    if Cout % 32:
+        assert float(y[..., Cout:].abs().max()) == 0.0
+
+
+def test_conv_fwd_matrix_mode_and_stats():
+    from cy4 import convops as co
+    torch.manual_seed(1)
+    B, H, W, Cin, Cout = 2, 38, 38, 64, 128
+    x = torch.randn(B, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, Cin, 1, 1, device="cuda") / 8).half()
+    wp = co.pack_fprop(w.float())
+    s1 = torch.zeros(Cout, device="cuda"); s2 = torch.zeros(Cout, device="cuda")
+    y = co.conv_fwd(x, wp, Cout, 1, 1, 0, stats=(s1, s2), a_matrix=True)
+    ref = _ref_conv(x, w, 1, 0)
+    assert (y.float().cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+    np.testing.assert_allclose(s1.cpu().numpy(), ref.sum((0, 1, 2)).numpy(), rtol=1e-3, atol=2e-2)
+    np.testing.assert_allclose(s2.cpu().numpy(), (ref * ref).sum((0, 1, 2)).numpy(), rtol=1e-3)
+
+
+def test_conv_fwd_f32_bias_and_slices():
+    """fp32 head output with bias; input read from / output written into channel slices (ld > C)."""
+    from cy4 import convops as co
+    torch.manual_seed(2)
+    B, H, W = 2, 19, 19
+    big = torch.randn(B, H, W, 192, device="cuda").half()
+    x = big[..., 64:192]                              # Cin=128 slice, ld=192
+    w = (torch.randn(30, 128, 1, 1, device="cuda") / 11).half()
+    bias = torch.randn(32, device="cuda"); bias[30:] = 0
+    y = co.conv_fwd(x, co.pack_fprop(w.float()), 30, 1, 1, 0, out_f32=True, bias=bias)
+    ref = _ref_conv(x.contiguous(), w, 1, 0) + bias[:30].cpu()
+    assert (y[..., :30].cpu() - ref).abs().max().item() < 2e-3
+    w2 = (torch.randn(64, 128, 3, 3, device="cuda") / 34).half()
+    outbuf = torch.zeros(B, H, W, 160, device="cuda", dtype=torch.float16)
+    co.conv_fwd(x, co.pack_fprop(w2.float()), 64, 3, 1, 1, out=outbuf[..., 96:160])
+    ref2 = _ref_conv(x.contiguous(), w2, 1, 1)
+    assert (outbuf[..., 96:160].float().cpu() - ref2).abs().max().item() <= 2e-3 * ref2.abs().max().item() + 1e-3
+    assert float(outbuf[..., :96].abs().max()) == 0.0
+
+
+def test_stem_path():
+    """3-channel stem: explicit im2col to [M,32] then the tensor-core GEMM (reference conv1)."""
+    from cy4 import convops as co
+    torch.manual_seed(3)
+    for stride in (1, 2):
+        x = torch.rand(2, 3, 64, 48, device="cuda")
+        w = torch.randn(32, 3, 3, 3, device="cuda") / 5
+        cols = co.stem_im2col(x, 3, stride, 1)
+        # weights in (r, s, c) order padded to 32
+        wp = torch.zeros(32, 32, device="cuda", dtype=torch.float16)
+        wp[:, :27] = w.permute(0, 2, 3, 1).reshape(32, 27).half()
+        y = co.conv_fwd(cols, wp, 32, 1, 1, 0, a_matrix=True)
+        ref = F.conv2d(x.half().float().cpu(), w.half().float().cpu(), None, stride, 1).permute(0, 2, 3, 1)
+        assert (y.float().cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
+DGRAD_CASES = [
+    (2, 19, 19, 64, 128, 1, 1),
+    (2, 38, 38, 64, 128, 3, 1),
+    (1, 19, 19, 256, 512, 3, 1),
+    (2, 38, 38, 64, 128, 3, 2),
+    (2, 40, 24, 32, 64, 3, 2),
+    (2, 76, 76, 128, 256, 3, 2),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", DGRAD_CASES)
+def test_conv_dgrad(B, H, W, Cin, Cout, k, stride):
+    from cy4 import convops as co
+    torch.manual_seed(B + H + Cin + Cout + k + stride)
+    pad = (k - 1) // 2
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    dy = torch.randn(B, Ho, Wo, Cout, device="cuda").half()
+    w = (torch.randn(Cout, Cin, k, k, device="cuda") / (Cout * k * k) ** 0.5).half()
+    dx = co.conv_dgrad(dy, co.pack_dgrad(w.float()), H, W, Cin, k, stride, pad)
+    x = torch.zeros(B, Cin, H, W, requires_grad=True)
+    yref = F.conv2d(x, w.float().cpu(), None, stride, pad)
+    yref.backward(dy.float().cpu().permute(0, 3, 1, 2))
+    ref = x.grad.permute(0, 2, 3, 1)
+    err = (dx.float().cpu() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, err
+    # accumulate mode: dx2 = dx + dgrad
+    dx2 = dx.clone()
+    co.conv_dgrad(dy, co.pack_dgrad(w.float()), H, W, Cin, k, stride, pad, out=dx2, accumulate=True)
+    assert (dx2.float().cpu() - 2 * ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 2e-3
+
+
+WGRAD_CASES = [
+    # B, H, W, Cin, Cout, k, stride
+    (2, 19, 19, 64, 128, 1, 1),
+    (2, 19, 19, 128, 64, 3, 1),      # Cout=64: second dY box out of range
+    (1, 38, 38, 256, 256, 3, 1),     # N=256 (4 boxes), M two tiles
+    (2, 38, 38, 64, 128, 3, 2),      # stride 2
+    (3, 19, 19, 512, 256, 1, 1),     # two n tiles
+    (2, 24, 40, 64, 64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", WGRAD_CASES)
+def test_conv_wgrad(B, H, W, Cin, Cout, k, stride):
+    from cy4 import convops as co
+    torch.manual_seed(B + H + Cin + Cout + k + stride + 5)
+    pad = (k - 1) // 2
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    x = torch.randn(B, H, W, Cin, device="cuda").half()
+    dy = (torch.randn(B, Ho, Wo, Cout, device="cuda") / (B * Ho * Wo) ** 0.5).half()
+    acc = co.conv_wgrad(x, dy, Cin, Cout, k, stride, pad)
+    gw = co.unpack_wgrad(acc, Cout, Cin, k)
+    w = torch.zeros(Cout, Cin, k, k, requires_grad=True)
+    y = F.conv2d(x.float().cpu().permute(0, 3, 1, 2), w, None, stride, pad)
+    y.backward(dy.float().cpu().permute(0, 3, 1, 2))
+    ref = w.grad
+    err = (gw.cpu() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
+
+
+def test_conv_wgrad_stem_and_narrow():
+    """Stem cols matrix (32 wide, 64B-swizzle B operand) and 32-channel tensors stored with ld=64."""
+    from cy4 import convops as co
+    torch.manual_seed(9)
+    xin = torch.rand(2, 3, 32, 48, device="cuda")
+    cols = co.stem_im2col(xin, 3, 1, 1)                              # [2,32,48,32]
+    dyb = torch.zeros(2, 32, 48, 64, device="cuda", dtype=torch.float16)
+    dyb[..., :32] = (torch.randn(2, 32, 48, 32, device="cuda") / 40).half()
+    acc = co.conv_wgrad(cols, dyb[..., :32], 32, 32, 1, 1, 0, a_matrix=True)
+    ref = torch.einsum("bhwo,bhwi->oi", dyb[..., :32].float().cpu(), cols.float().cpu())
+    assert (acc[:32, 0, :].cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-4
+    # 32-channel activation kept in a 64-wide buffer (pad channels arbitrary but finite)
+    xb = torch.randn(2, 20, 20, 64, device="cuda").half()
+    dy2 = torch.zeros(2, 20, 20, 64, device="cuda", dtype=torch.float16)
+    dy2[..., :64] = (torch.randn(2, 20, 20, 64, device="cuda") / 28).half()
+    acc2 = co.conv_wgrad(xb[..., :32], dy2, 32, 64, 3, 1, 1)
+    w = torch.zeros(64, 32, 3, 3, requires_grad=True)
+    y = F.conv2d(xb[..., :32].float().cpu().permute(0, 3, 1, 2), w, None, 1, 1)
+    y.backward(dy2.float().cpu().permute(0, 3, 1, 2))
+    gw = co.unpack_wgrad(acc2, 64, 32, 3)
+    assert (gw.cpu() - w.grad).abs().max().item() <= 2e-3 * w.grad.abs().max().item() + 1e-4
