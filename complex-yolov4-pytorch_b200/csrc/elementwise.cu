@@ -1,0 +1,489 @@
+// elementwise.cu -- the bandwidth-bound part of the network on NHWC fp16 tensors with an explicit
+// channel stride (ld): BatchNorm (training statistics come fused out of the conv epilogue) + Mish /
+// LeakyReLU forward and backward, shortcut adds, route (concat / slice) copies, SPP max pooling,
+// nearest upsampling, dtype/scale conversions.  All kernels move 16-byte vectors (8 halves).
+// Reference ops replaced: nn.BatchNorm2d, Mish, nn.LeakyReLU, torch.cat, shortcut add, nn.MaxPool2d,
+// Upsample_expand in src/models/darknet2pytorch.py:22-28,64-79,180-219,256-285.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace cy4 {
+
+enum { ACT_LINEAR = 0, ACT_LEAKY = 1, ACT_MISH = 2 };
+
+// mish(z) = z * tanh(softplus(z));  tanh(log(1+e^z)) = n / (n + 2),  n = e^z (e^z + 2).
+// softplus threshold 20 as torch (F.softplus): beyond it tanh(.) == 1 in fp32.
+__device__ __forceinline__ float mish_f(float z)
+{
+    if (z > 20.f) return z;
+    const float e = __expf(z);
+    const float n = e * (e + 2.f);
+    return z * __fdividef(n, n + 2.f);
+}
+// d mish / dz = t + z * t',  t = n/(n+2),  t' = 4 e (e + 1) / (n + 2)^2
+__device__ __forceinline__ float mish_grad_f(float z)
+{
+    if (z > 20.f) return 1.f;
+    const float e = __expf(z);
+    const float n = e * (e + 2.f);
+    const float inv = __fdividef(1.f, n + 2.f);
+    return n * inv + z * 4.f * e * (e + 1.f) * inv * inv;
+}
+__device__ __forceinline__ float act_f(float z, int act)
+{
+    return act == ACT_MISH ? mish_f(z) : (act == ACT_LEAKY ? (z > 0.f ? z : 0.1f * z) : z);
+}
+__device__ __forceinline__ float act_grad_f(float z, int act)
+{
+    return act == ACT_MISH ? mish_grad_f(z) : (act == ACT_LEAKY ? (z > 0.f ? 1.f : 0.1f) : 1.f);
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &v, float f[8])
+{
+    const __half2 *h = (const __half2 *)&v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float f[8])
+{
+    uint4 v; __half2 *h = (__half2 *)&v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+
+// ---- BatchNorm statistics -> per-channel scale / shift ------------------------------------------
+__global__ void bn_finalize_kernel(const float *__restrict__ ch_sum, const float *__restrict__ ch_sqsum, float count,
+                                   const float *__restrict__ gamma, const float *__restrict__ beta, float *running_mean,
+                                   float *running_var, long long *num_batches, float momentum, float eps, int training, int C,
+                                   float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
+                                   float *__restrict__ rstd_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && num_batches) *num_batches += 1;
+    if (c >= C) return;
+    float mean, var;
+    if (training) {
+        const double m = (double)ch_sum[c] / count;
+        double v = (double)ch_sqsum[c] / count - m * m;
+        if (v < 0.0) v = 0.0;
+        mean = (float)m; var = (float)v;
+        const float unbiased = count > 1.f ? (float)(v * (double)count / ((double)count - 1.0)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    } else {
+        mean = running_mean[c]; var = running_var[c];
+    }
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+}
+
+// out = act(y * scale + shift) (+ residual)
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__restrict__ scale, const float *__restrict__ shift, int act,
+                  const __half *__restrict__ res, int64_t ldr, __half *__restrict__ out, int64_t ldo, int64_t M, int C)
+{
+    const int vpr = C >> 3;
+    const int64_t total = M * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / vpr;
+        const int c0 = (int)(i - m * vpr) << 3;
+        float f[8], r[8];
+        unpack8(*(const uint4 *)(y + m * ldy + c0), f);
+        const float4 s0 = __ldg((const float4 *)(scale + c0)), s1 = __ldg((const float4 *)(scale + c0 + 4));
+        const float4 h0 = __ldg((const float4 *)(shift + c0)), h1 = __ldg((const float4 *)(shift + c0 + 4));
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = act_f(fmaf(f[k], sc[k], sh[k]), act);
+        if (res) {
+            unpack8(*(const uint4 *)(res + m * ldr + c0), r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += r[k];
+        }
+        *(uint4 *)(out + m * ldo + c0) = pack8(f);
+    }
+}
+
+// Per-channel sums of dz = dA * act'(z) and dz * xhat  (xhat = (y - mean) * rstd).
+// Thread = one 8-channel vector column, striding over rows; block partials via shared memory;
+// one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
+                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
+                         const float *__restrict__ rstd, int act, int64_t M, int C, float *__restrict__ sum_dz,
+                         float *__restrict__ sum_dzx)
+{
+    const int vpr = C >> 3;                       // vectors per row
+    const int rows_per_it = 256 / min(vpr, 256);  // rows a block covers per iteration (vpr <= 256 handled below)
+    __shared__ float red[2][256][8 + 1];
+    for (int v0 = 0; v0 < vpr; v0 += 256) {
+        const int nv = min(256, vpr - v0);
+        const int rpi = 256 / nv;
+        const int vec = threadIdx.x % nv, rsub = threadIdx.x / nv;
+        float a1[8], a2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+        if (rsub < rpi) {
+            const int c0 = (v0 + vec) << 3;
+            float sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; }
+            for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += (int64_t)gridDim.x * rpi) {
+                float fy[8], fg[8];
+                unpack8(*(const uint4 *)(y + m * ldy + c0), fy);
+                unpack8(*(const uint4 *)(dA + m * ldg + c0), fg);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float z = fmaf(fy[k], sc[k], sh[k]);
+                    const float dz = fg[k] * act_grad_f(z, act);
+                    a1[k] += dz;
+                    a2[k] += dz * ((fy[k] - mu[k]) * rs[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { red[0][threadIdx.x][k] = a1[k]; red[1][threadIdx.x][k] = a2[k]; }
+        __syncthreads();
+        // threads 0 .. nv*8-1 : channel (t>>3 vector, t&7 lane) sums over the rpi row groups
+        for (int t = threadIdx.x; t < nv * 8; t += 256) {
+            const int vv = t >> 3, kk = t & 7;
+            float s1 = 0.f, s2 = 0.f;
+            for (int r = 0; r < rpi; ++r) { s1 += red[0][r * nv + vv][kk]; s2 += red[1][r * nv + vv][kk]; }
+            atomicAdd(sum_dz + ((v0 + vv) << 3) + kk, s1);
+            atomicAdd(sum_dzx + ((v0 + vv) << 3) + kk, s2);
+        }
+        __syncthreads();
+    }
+    (void)rows_per_it;
+}
+
+// dY = scale * (dz - sum_dz/M - xhat * sum_dzx/M)   (training-mode BN backward; eval: dY = scale*dz)
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
+                        const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
+                        const float *__restrict__ rstd, const float *__restrict__ sum_dz, const float *__restrict__ sum_dzx,
+                        float inv_count, int training, int act, __half *__restrict__ dY, int64_t ldd, int64_t M, int C)
+{
+    const int vpr = C >> 3;
+    const int64_t total = M * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / vpr;
+        const int c0 = (int)(i - m * vpr) << 3;
+        float fy[8], fg[8], o[8];
+        unpack8(*(const uint4 *)(y + m * ldy + c0), fy);
+        unpack8(*(const uint4 *)(dA + m * ldg + c0), fg);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + k;
+            const float sc = __ldg(scale + c);
+            const float z = fmaf(fy[k], sc, __ldg(shift + c));
+            const float dz = fg[k] * act_grad_f(z, act);
+            if (training) {
+                const float xh = (fy[k] - __ldg(mean + c)) * __ldg(rstd + c);
+                o[k] = sc * (dz - __ldg(sum_dz + c) * inv_count - xh * __ldg(sum_dzx + c) * inv_count);
+            } else {
+                o[k] = sc * dz;
+            }
+        }
+        *(uint4 *)(dY + m * ldd + c0) = pack8(o);
+    }
+}
+
+// out = a (+ b)      (copy / add over channel slices; also gradient accumulation)
+__global__ void __launch_bounds__(256)
+add_copy_kernel(const __half *__restrict__ a, int64_t lda, const __half *__restrict__ b, int64_t ldb, __half *__restrict__ out,
+                int64_t ldo, int64_t M, int C)
+{
+    const int vpr = C >> 3;
+    const int64_t total = M * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / vpr;
+        const int c0 = (int)(i - m * vpr) << 3;
+        uint4 va = *(const uint4 *)(a + m * lda + c0);
+        if (b) {
+            float fa[8], fb[8];
+            unpack8(va, fa);
+            unpack8(*(const uint4 *)(b + m * ldb + c0), fb);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+            va = pack8(fa);
+        }
+        *(uint4 *)(out + m * ldo + c0) = va;
+    }
+}
+
+// nearest x2 upsample: out[b, 2h+i, 2w+j, c] = in[b, h, w, c]
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const __half *__restrict__ in, int64_t ldi, __half *__restrict__ out, int64_t ldo, int B, int H, int W, int C)
+{
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * (2 * H) * (2 * W) * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
+        const int ow = (int)(r % (2 * W)); r /= (2 * W);
+        const int oh = (int)(r % (2 * H));
+        const int b = (int)(r / (2 * H));
+        const int64_t src = ((int64_t)b * H + (oh >> 1)) * W + (ow >> 1);
+        const int64_t dst = ((int64_t)b * 2 * H + oh) * (2 * W) + ow;
+        *(uint4 *)(out + dst * ldo + c0) = *(const uint4 *)(in + src * ldi + c0);
+    }
+}
+// gin[b,h,w,c] (+)= sum of the 2x2 block of gout
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const __half *__restrict__ gout, int64_t ldo, __half *__restrict__ gin, int64_t ldi, int B, int H, int W, int C,
+                      int accumulate)
+{
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * H * W * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        float acc[8], t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                const int64_t src = ((int64_t)b * 2 * H + 2 * h + dy) * (2 * W) + 2 * w + dx;
+                unpack8(*(const uint4 *)(gout + src * ldo + c0), t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += t[k];
+            }
+        __half *dst = gin + (((int64_t)b * H + h) * W + w) * ldi + c0;
+        if (accumulate) {
+            unpack8(*(const uint4 *)dst, t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += t[k];
+        }
+        *(uint4 *)dst = pack8(acc);
+    }
+}
+
+// max pooling, window k, stride s, symmetric pad (nn.MaxPool2d(k, s, k//2) for s == 1, pad 0 for k == s)
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const __half *__restrict__ in, int64_t ldi, __half *__restrict__ out, int64_t ldo, int B, int H, int W, int C,
+                   int k, int s, int pad, int Ho, int Wo)
+{
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * Ho * Wo * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
+        const int ow = (int)(r % Wo); r /= Wo;
+        const int oh = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        float best[8], t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) best[q] = -INFINITY;
+        for (int dy = 0; dy < k; ++dy) {
+            const int h = oh * s - pad + dy;
+            if (h < 0 || h >= H) continue;
+            for (int dx = 0; dx < k; ++dx) {
+                const int w = ow * s - pad + dx;
+                if (w < 0 || w >= W) continue;
+                unpack8(*(const uint4 *)(in + (((int64_t)b * H + h) * W + w) * ldi + c0), t);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) best[q] = fmaxf(best[q], t[q]);
+            }
+        }
+        *(uint4 *)(out + (((int64_t)b * Ho + oh) * Wo + ow) * ldo + c0) = pack8(best);
+    }
+}
+// gradient: each output pixel routes its gradient to the FIRST maximal element of its window
+// (torch's scan order), accumulated in an fp32 scratch [B,H,W,C] with atomics.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __half *__restrict__ in, int64_t ldi, const __half *__restrict__ gout, int64_t ldo, float *__restrict__ gscratch,
+                   int B, int H, int W, int C, int k, int s, int pad, int Ho, int Wo)
+{
+    const int64_t total = (int64_t)B * Ho * Wo * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        const int ow = (int)(r % Wo); r /= Wo;
+        const int oh = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        float best = -INFINITY; int bh = -1, bw = -1;
+        for (int dy = 0; dy < k; ++dy) {
+            const int h = oh * s - pad + dy;
+            if (h < 0 || h >= H) continue;
+            for (int dx = 0; dx < k; ++dx) {
+                const int w = ow * s - pad + dx;
+                if (w < 0 || w >= W) continue;
+                const float v = __half2float(in[(((int64_t)b * H + h) * W + w) * ldi + c]);
+                if (v > best || bh < 0) { best = v; bh = h; bw = w; }
+            }
+        }
+        const float g = __half2float(gout[(((int64_t)b * Ho + oh) * Wo + ow) * ldo + c]);
+        if (bh >= 0) atomicAdd(gscratch + (((int64_t)b * H + bh) * W + bw) * C + c, g);
+    }
+}
+// gin (+)= fp32 scratch
+__global__ void __launch_bounds__(256)
+f32_to_f16_accum_kernel(const float *__restrict__ src, int64_t lds, float scale, __half *__restrict__ dst, int64_t ldd, int64_t M, int C,
+                        int accumulate)
+{
+    const int vpr = C >> 3;
+    const int64_t total = M * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / vpr;
+        const int c0 = (int)(i - m * vpr) << 3;
+        const float4 a = *(const float4 *)(src + m * lds + c0), b = *(const float4 *)(src + m * lds + c0 + 4);
+        float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+        __half *d = dst + m * ldd + c0;
+        if (accumulate) {
+            float t[8];
+            unpack8(*(const uint4 *)d, t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += t[k];
+        }
+        *(uint4 *)d = pack8(f);
+    }
+}
+
+// per-channel column sums of a fp32 [M, ld] matrix (bias gradient of the head convs)
+__global__ void colsum_f32_kernel(const float *__restrict__ src, int64_t lds, int64_t M, int C, float scale, float *__restrict__ out, int accumulate)
+{
+    const int c = blockIdx.x;
+    __shared__ float red[256];
+    float a = 0.f;
+    for (int64_t m = threadIdx.x; m < M; m += 256) a += src[m * lds + c];
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0 && c < C) out[c] = (accumulate ? out[c] : 0.f) + red[0] * scale;
+}
+
+static inline int ew_grid(int64_t total)
+{
+    const int64_t need = (total + 255) / 256;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 16));
+}
+
+}  // namespace cy4
+
+using namespace cy4;
+
+#define EW_CHECK_C(C, who) CY4_CHECK_ARG((C) > 0 && ((C) % 8) == 0, who ": channels must be a positive multiple of 8")
+
+extern "C" {
+
+int cy4_bn_finalize(const float *ch_sum, const float *ch_sqsum, float count, const float *gamma, const float *beta,
+                    float *running_mean, float *running_var, int64_t *num_batches_tracked, float momentum, float eps,
+                    int training, int C, float *scale, float *shift, float *mean, float *rstd, void *stream)
+{
+    CY4_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && mean && rstd && C > 0 &&
+                  (!training || (ch_sum && ch_sqsum && count > 0)), "cy4_bn_finalize: bad argument");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ch_sum, ch_sqsum, count, gamma, beta, running_mean, running_var,
+                                                                         (long long *)num_batches_tracked, momentum, eps, training, C,
+                                                                         scale, shift, mean, rstd);
+    return cy4_launch_status("cy4_bn_finalize");
+}
+
+int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *shift, int act, const void *residual, int64_t ldr,
+                   void *out, int64_t ldo, int64_t M, int C, void *stream)
+{
+    EW_CHECK_C(C, "cy4_bn_act_fwd");
+    CY4_CHECK_ARG(y && scale && shift && out && M >= 0 && (ldy % 8) == 0 && (ldo % 8) == 0 && (ldr % 8) == 0, "cy4_bn_act_fwd: bad argument");
+    if (M == 0) return 0;
+    bn_act_fwd_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, act, (const __half *)residual,
+                                                                              ldr, (__half *)out, ldo, M, C);
+    return cy4_launch_status("cy4_bn_act_fwd");
+}
+
+int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
+                          const float *mean, const float *rstd, int act, int64_t M, int C, float *sum_dz, float *sum_dzx, void *stream)
+{
+    EW_CHECK_C(C, "cy4_bn_act_bwd_reduce");
+    CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && M >= 0, "cy4_bn_act_bwd_reduce: bad argument");
+    if (M == 0) return 0;
+    const int vpr = C / 8;
+    const int rpi = std::max(1, 256 / std::min(vpr, 256));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((M + rpi - 1) / rpi, (int64_t)sm_count() * 8));
+    bn_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift, mean, rstd,
+                                                                     act, M, C, sum_dz, sum_dzx);
+    return cy4_launch_status("cy4_bn_act_bwd_reduce");
+}
+
+int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
+                         const float *mean, const float *rstd, const float *sum_dz, const float *sum_dzx, float inv_count,
+                         int training, int act, void *dY, int64_t ldd, int64_t M, int C, void *stream)
+{
+    EW_CHECK_C(C, "cy4_bn_act_bwd_apply");
+    CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && dY && M >= 0, "cy4_bn_act_bwd_apply: bad argument");
+    if (M == 0) return 0;
+    bn_act_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift,
+                                                                                    mean, rstd, sum_dz, sum_dzx, inv_count, training, act,
+                                                                                    (__half *)dY, ldd, M, C);
+    return cy4_launch_status("cy4_bn_act_bwd_apply");
+}
+
+int cy4_add_copy(const void *a, int64_t lda, const void *b, int64_t ldb, void *out, int64_t ldo, int64_t M, int C, void *stream)
+{
+    EW_CHECK_C(C, "cy4_add_copy");
+    CY4_CHECK_ARG(a && out && M >= 0 && (lda % 8) == 0 && (ldo % 8) == 0 && (ldb % 8) == 0, "cy4_add_copy: bad argument");
+    if (M == 0) return 0;
+    add_copy_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)a, lda, (const __half *)b, ldb, (__half *)out, ldo, M, C);
+    return cy4_launch_status("cy4_add_copy");
+}
+
+int cy4_upsample2x_fwd(const void *in, int64_t ldi, void *out, int64_t ldo, int B, int H, int W, int C, void *stream)
+{
+    EW_CHECK_C(C, "cy4_upsample2x_fwd");
+    CY4_CHECK_ARG(in && out, "cy4_upsample2x_fwd: null pointer");
+    upsample2x_fwd_kernel<<<ew_grid((int64_t)B * 4 * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (__half *)out, ldo, B, H, W, C);
+    return cy4_launch_status("cy4_upsample2x_fwd");
+}
+
+int cy4_upsample2x_bwd(const void *gout, int64_t ldo, void *gin, int64_t ldi, int B, int H, int W, int C, int accumulate, void *stream)
+{
+    EW_CHECK_C(C, "cy4_upsample2x_bwd");
+    CY4_CHECK_ARG(gout && gin, "cy4_upsample2x_bwd: null pointer");
+    upsample2x_bwd_kernel<<<ew_grid((int64_t)B * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)gout, ldo, (__half *)gin, ldi, B, H, W, C, accumulate);
+    return cy4_launch_status("cy4_upsample2x_bwd");
+}
+
+int cy4_maxpool_fwd(const void *in, int64_t ldi, void *out, int64_t ldo, int B, int H, int W, int C, int k, int stride, int pad, void *stream)
+{
+    EW_CHECK_C(C, "cy4_maxpool_fwd");
+    CY4_CHECK_ARG(in && out && k > 0 && stride > 0, "cy4_maxpool_fwd: bad argument");
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    maxpool_fwd_kernel<<<ew_grid((int64_t)B * Ho * Wo * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (__half *)out, ldo, B, H, W, C, k, stride, pad, Ho, Wo);
+    return cy4_launch_status("cy4_maxpool_fwd");
+}
+
+int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C, int k,
+                    int stride, int pad, void *stream)
+{
+    CY4_CHECK_ARG(in && gout && gscratch && k > 0 && stride > 0, "cy4_maxpool_bwd: bad argument");
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    maxpool_bwd_kernel<<<ew_grid((int64_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (const __half *)gout, ldo, gscratch,
+                                                                                            B, H, W, C, k, stride, pad, Ho, Wo);
+    return cy4_launch_status("cy4_maxpool_bwd");
+}
+
+int cy4_f32_to_f16(const float *src, int64_t lds, float scale, void *dst, int64_t ldd, int64_t M, int C, int accumulate, void *stream)
+{
+    EW_CHECK_C(C, "cy4_f32_to_f16");
+    CY4_CHECK_ARG(src && dst && M >= 0 && (lds % 4) == 0 && (ldd % 8) == 0, "cy4_f32_to_f16: bad argument");
+    if (M == 0) return 0;
+    f32_to_f16_accum_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(src, lds, scale, (__half *)dst, ldd, M, C, accumulate);
+    return cy4_launch_status("cy4_f32_to_f16");
+}
+
+int cy4_colsum_f32(const float *src, int64_t lds, int64_t M, int C, float scale, float *out, int accumulate, void *stream)
+{
+    CY4_CHECK_ARG(src && out && M >= 0 && C > 0, "cy4_colsum_f32: bad argument");
+    colsum_f32_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(src, lds, M, C, scale, out, accumulate);
+    return cy4_launch_status("cy4_colsum_f32");
+}
+
+}  // extern "C"

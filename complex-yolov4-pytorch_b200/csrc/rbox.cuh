@@ -25,10 +25,17 @@ struct PolySmem {
     signed char s[2][kMaxV][BLOCK];
 };
 
+// atan2 evaluated in fp64 and rounded once (see box_corners).
+__device__ __forceinline__ float atan2_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
+
 __device__ __forceinline__ void box_corners(float x, float y, float w, float l, float yaw,
                                             float cx[4], float cy[4], float &cs, float &sn)
 {
-    cs = cosf(yaw); sn = sinf(yaw);
+    // fp64 sincos rounded once to fp32: correctly rounded like glibc / (almost always) Sleef, so the
+    // corner coordinates are bit-identical to the reference's for the vast majority of boxes.
+    double sd, cd;
+    sincos((double)yaw, &sd, &cd);
+    cs = (float)cd; sn = (float)sd;
     const float hw = w / 2.0f, hl = l / 2.0f;
     const float a = hw * cs, b = hl * sn, c = hw * sn, d = hl * cs;
     cx[0] = (x - a) - b;  cy[0] = (y - c) + d;   // front left
@@ -162,9 +169,9 @@ __device__ __forceinline__ void rgiou_pair(const float P[6], const float T[6], b
 {
     float px[4], py[4], tx[4], ty[4], tcs, tsn;
     CornerGrad cg;
-    const float tyaw = atan2f(T[4], T[5]);
+    const float tyaw = atan2_cr(T[4], T[5]);
     box_corners(T[0], T[1], T[2], T[3], tyaw, tx, ty, tcs, tsn);
-    const float pyaw = atan2f(P[4], P[5]);
+    const float pyaw = atan2_cr(P[4], P[5]);
     box_corners(P[0], P[1], P[2], P[3], pyaw, px, py, cg.cs, cg.sn);
     cg.hw = 0.5f * P[2]; cg.hl = 0.5f * P[3];
     const float t_area = T[2] * T[3];
@@ -303,8 +310,8 @@ __device__ __forceinline__ void rgiou_pair(const float P[6], const float T[6], b
 __device__ inline float anchor_target_iou(const float A[4], const float T[4])
 {
     float ax[4], ay[4], bx[4], by[4], cs, sn;
-    box_corners(100.0f, 100.0f, A[0], A[1], atan2f(A[2], A[3]), ax, ay, cs, sn);
-    box_corners(100.0f, 100.0f, T[0], T[1], atan2f(T[2], T[3]), bx, by, cs, sn);
+    box_corners(100.0f, 100.0f, A[0], A[1], atan2_cr(A[2], A[3]), ax, ay, cs, sn);
+    box_corners(100.0f, 100.0f, T[0], T[1], atan2_cr(T[2], T[3]), bx, by, cs, sn);
     const float aa = A[0] * A[1], ta = T[0] * T[1];
     const float inter = (float)convex_inter64(ax, ay, bx, by);
     const float den = ((aa + ta) - inter) + 1e-16f;

@@ -159,6 +159,43 @@ CY4_API int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, 
 CY4_API int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int ksize, int stride, int pad,
                             void *cols /* [B*Ho*Wo, 32] fp16 */, void *stream);
 
+/* ---- bandwidth-bound layers on NHWC fp16 (channel stride ld, channels % 8 == 0) -------------------
+ * Replace nn.BatchNorm2d / Mish / nn.LeakyReLU / torch.cat / shortcut add / nn.MaxPool2d /
+ * Upsample_expand of models/darknet2pytorch.py:22-28,64-79,180-219,256-285 and their backward. */
+#define CY4_ACT_LINEAR 0
+#define CY4_ACT_LEAKY  1   /* LeakyReLU(0.1), darknet2pytorch.py:265-266 */
+#define CY4_ACT_MISH   2   /* x * tanh(softplus(x)), darknet2pytorch.py:22-28 */
+
+/* Batch statistics (sum / sum of squares from cy4_conv_fwd, count = B*H*W) -> per-channel
+ * scale = gamma*rstd, shift = beta - mean*scale; training also updates running_mean/var (momentum,
+ * unbiased variance) and num_batches_tracked exactly like nn.BatchNorm2d; training=0 uses them. */
+CY4_API int cy4_bn_finalize(const float *ch_sum, const float *ch_sqsum, float count, const float *gamma, const float *beta,
+                            float *running_mean, float *running_var, int64_t *num_batches_tracked, float momentum, float eps,
+                            int training, int C, float *scale, float *shift, float *mean, float *rstd, void *stream);
+/* out = act(y*scale + shift) (+ residual) */
+CY4_API int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *shift, int act, const void *residual,
+                           int64_t ldr, void *out, int64_t ldo, int64_t M, int C, void *stream);
+/* sum_dz[c] += sum_m dA*act'(z), sum_dzx[c] += sum_m dA*act'(z)*xhat  (= d beta, d gamma) */
+CY4_API int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
+                                  const float *mean, const float *rstd, int act, int64_t M, int C, float *sum_dz, float *sum_dzx,
+                                  void *stream);
+/* dY = scale*(dz - sum_dz/M - xhat*sum_dzx/M) (training) or scale*dz (eval) */
+CY4_API int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
+                                 const float *mean, const float *rstd, const float *sum_dz, const float *sum_dzx, float inv_count,
+                                 int training, int act, void *dY, int64_t ldd, int64_t M, int C, void *stream);
+/* out = a (+ b): route copies into / out of concat buffers, shortcut add, gradient accumulation */
+CY4_API int cy4_add_copy(const void *a, int64_t lda, const void *b, int64_t ldb, void *out, int64_t ldo, int64_t M, int C, void *stream);
+CY4_API int cy4_upsample2x_fwd(const void *in, int64_t ldi, void *out, int64_t ldo, int B, int H, int W, int C, void *stream);
+CY4_API int cy4_upsample2x_bwd(const void *gout, int64_t ldo, void *gin, int64_t ldi, int B, int H, int W, int C, int accumulate, void *stream);
+CY4_API int cy4_maxpool_fwd(const void *in, int64_t ldi, void *out, int64_t ldo, int B, int H, int W, int C, int k, int stride, int pad, void *stream);
+/* gscratch [B,H,W,C] fp32 (caller-zeroed) += routed gradients; follow with cy4_f32_to_f16 */
+CY4_API int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C,
+                            int k, int stride, int pad, void *stream);
+/* dst (+)= fp16(scale * src) */
+CY4_API int cy4_f32_to_f16(const float *src, int64_t lds, float scale, void *dst, int64_t ldd, int64_t M, int C, int accumulate, void *stream);
+/* out[c] (+)= scale * sum_m src[m, c]  (bias gradient of the head convs) */
+CY4_API int cy4_colsum_f32(const float *src, int64_t lds, int64_t M, int C, float scale, float *out, int accumulate, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
