@@ -163,7 +163,7 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     const int k = d->ksize;
     const int cout64 = (d->Cout + 63) / 64 * 64;
     CY4_CHECK_ARG(d->ldy >= cout64 && d->ldy % 8 == 0, "cy4_conv_wgrad: dy must be allocated with ld >= Cout rounded up to 64");
-    const bool sw64 = d->Cin == 32 && d->ldx < 64;
+    const bool sw64 = d->Cin == 32;     // one [64 px x 32 ch] box, 64B swizzle: never reads past the 32 channels
     const int cin64 = sw64 ? 32 : (d->Cin + 63) / 64 * 64;
     CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx >= cin64 && d->ldx % 8 == 0, "cy4_conv_wgrad: x must be allocated with ld >= Cin rounded up to 64 (or Cin == 32)");
     WgradParams p;

@@ -1,0 +1,619 @@
+"""Step engine: executes the Darknet graph (reference src/models/darknet2pytorch.py:162-230 forward
+interpreter + autograd backward) as a static plan of hand-written sm_100a kernels.
+
+Layout in HBM (per plan = per input shape):
+  * every activation is NHWC fp16 in its own [B*H*W, ld] buffer, ld = channels rounded up to 64
+    (so that the weight-gradient TMA boxes never leave the allocation);
+  * each conv keeps its raw output Y (pre-BatchNorm) and the activated output A; backward
+    recomputes BN/activation derivatives from Y instead of storing them;
+  * per-channel BN quantities (batch sums, scale/shift, mean/rstd, d gamma, d beta) of ALL layers
+    live in a few flat fp32 buffers, zeroed with one memset per step;
+  * fp32 master weights stay in the nn.Parameters; K-major fp16 packs for fprop / dgrad are rebuilt
+    when the parameter version changes; weight gradients are accumulated in fp32 ([Cout][tap][Cin])
+    and unpacked into one flat OIHW gradient buffer whose slices are returned as the .grad tensors;
+  * gradient tensors are fp16 scaled by `model.grad_scale` (static loss scale, undone in fp32).
+
+The whole network + loss is ONE autograd node (`_NetFn`): train.py's `loss.backward()` runs the
+backward plan, DDP sees ordinary parameter gradients.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import convops as co
+from .yolo import LazyMetrics, make_desc, check_status
+
+ACT = {"linear": 0, "leaky": 1, "mish": 2}
+
+
+def rup(x, m):
+    return (x + m - 1) // m * m
+
+
+class Storage:
+    """An NHWC fp16 tensor [B,H,W,ld] (+ its gradient buffer)."""
+
+    def __init__(self, B, H, W, C, device, dtype=torch.float16, ld=None):
+        self.B, self.H, self.W, self.C = B, H, W, C
+        self.ld = ld or rup(C, 64)
+        self.M = B * H * W
+        self.buf = torch.zeros(B, H, W, self.ld, device=device, dtype=dtype)
+        self.grad = None
+        self.gstate = 0          # 0: gradient not written yet in this backward pass
+        self.partial = False     # some consumer writes only a channel slice -> memset first
+
+    def ensure_grad(self):
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.buf)
+        return self.grad
+
+
+class View:
+    """Channels [off, off+C) of a storage."""
+
+    def __init__(self, st, off=0, C=None):
+        self.st, self.off, self.C = st, off, (st.C if C is None else C)
+
+    @property
+    def ptr(self):
+        return self.st.buf.data_ptr() + self.off * self.st.buf.element_size()
+
+    @property
+    def gptr(self):
+        return self.st.ensure_grad().data_ptr() + self.off * 2
+
+    @property
+    def ld(self):
+        return self.st.ld
+
+
+class _NetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, x, targets, *params):
+        loss = eng._forward(x, targets)
+        ctx.eng = eng
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        grads = ctx.eng._backward(gloss)
+        return (None, None, None) + tuple(grads)
+
+
+class StepEngine:
+    def __init__(self, model):
+        self.model = model
+        self.plan = None
+        self.key = None
+        self.L = None
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, x, targets):
+        _lib.require_device()
+        self.L = _lib.lib()
+        model = self.model
+        dev_in = x.device
+        if not x.is_cuda:
+            x = x.cuda()
+            if targets is not None:
+                targets = targets.cuda()
+        params = [p for p in model.parameters()]
+        if params and params[0].device != x.device:
+            raise RuntimeError("Darknet parameters are on %s but the input is on %s" % (params[0].device, x.device))
+        training_graph = targets is not None and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        key = (tuple(x.shape), x.device, model.training, targets is not None,
+               tuple(p.data_ptr() for p in params[:4]), len(params))
+        with torch.cuda.device(x.device):
+            if self.key != key:
+                self.plan = Plan(model, x.shape, x.device, self.L)
+                self.key = key
+            self.plan.params = params
+            if targets is None:
+                with torch.no_grad():
+                    self._forward(x, None)
+                return self.plan.outputs().to("cpu")      # reference: to_cpu(torch.cat(yolo_outputs, 1))
+            if training_graph:
+                loss = _NetFn.apply(self, x, targets, *params)
+            else:
+                with torch.no_grad():
+                    loss = self._forward(x, targets)
+            out = self.plan.outputs()
+            if model.sync_outputs or not model.training:
+                out_cpu = out.to("cpu")
+            else:
+                # asynchronous copy into pinned memory: complete at the next stream sync
+                # (train.py reads loss.item() every step, which is such a sync)
+                out_cpu = self.plan.pinned_out(out)
+                out_cpu.copy_(out, non_blocking=True)
+            return loss, out_cpu
+
+    def _forward(self, x, targets):
+        return self.plan.forward(x, targets, self.model.use_giou_loss)
+
+    def _backward(self, gloss):
+        return self.plan.backward(gloss)
+
+
+class Plan:
+    """Buffers + op lists for one (batch, height, width) on one device."""
+
+    def __init__(self, model, xshape, device, L):
+        self.L = L
+        self.model = model
+        self.device = device
+        self.B, cin, self.H, self.W = xshape
+        assert cin == 3, "the BEV input has 3 channels"
+        self.S = float(model.grad_scale)
+        self.fwd_ops, self.bwd_ops = [], []
+        self.params = None
+        self._pinned = None
+        self._build()
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _call(self, fn, *args):
+        rc = fn(*args)
+        if rc < 0:
+            _lib.check(rc, fn.__name__)
+
+    def _build(self):
+        model, L, dev, B = self.model, self.L, self.device, self.B
+        blocks = model.blocks
+        outs = {}                       # layer index -> View
+        self.convs = []                 # per conv layer records
+        self.yolos = []
+        cur = None                      # current View (None = the network input)
+        cur_hw = (self.H, self.W)
+        totalC = 0
+        ind = -2
+        # pass 1: create storages / records
+        for block in blocks:
+            ind += 1
+            t = block["type"]
+            if t == "net":
+                continue
+            if t == "convolutional":
+                seq = model.models[ind]
+                conv = seq[0]
+                bn = seq[1] if int(block["batch_normalize"]) else None
+                k, stride = int(block["size"]), int(block["stride"])
+                pad = (k - 1) // 2 if int(block["pad"]) else 0
+                Cout = int(block["filters"])
+                Hi, Wi = cur_hw
+                Ho, Wo = (Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1
+                rec = dict(ind=ind, conv=conv, bn=bn, k=k, stride=stride, pad=pad, Cout=Cout, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo,
+                           act=ACT.get(block["activation"], 0), src=cur, stem=cur is None, Cin=conv.in_channels)
+                if block["activation"] not in ACT:
+                    raise NotImplementedError("activation %s" % block["activation"])
+                if rec["stem"]:
+                    assert conv.in_channels * k * k <= 32, "stem conv must have C*k*k <= 32"
+                    rec["cols"] = Storage(B, Ho, Wo, 32, dev, ld=32)
+                if bn is not None:
+                    rec["Y"] = Storage(B, Ho, Wo, Cout, dev)
+                    rec["A"] = Storage(B, Ho, Wo, Cout, dev)
+                    rec["coff"] = totalC
+                    totalC += rup(Cout, 8)
+                    cur = View(rec["A"])
+                else:
+                    rec["P"] = Storage(B, Ho, Wo, rup(Cout, 32), dev, dtype=torch.float32, ld=rup(Cout, 32))
+                    rec["dP"] = torch.zeros_like(rec["P"].buf)
+                    cur = View(rec["P"])
+                self.convs.append(rec)
+                cur_hw = (Ho, Wo)
+                outs[ind] = cur
+            elif t == "route":
+                layers = [int(i) if int(i) > 0 else int(i) + ind for i in block["layers"].split(",")]
+                if len(layers) == 1:
+                    src = outs[layers[0]]
+                    g = int(block.get("groups", 1))
+                    if g == 1:
+                        cur = src
+                    else:
+                        gid = int(block["group_id"])
+                        cg = src.C // g
+                        cur = View(src.st, src.off + cg * gid, cg)
+                        src.st.partial = True
+                else:
+                    srcs = [outs[l] for l in layers]
+                    st0 = srcs[0].st
+                    cat = Storage(B, st0.H, st0.W, sum(s.C for s in srcs), dev)
+                    off = 0
+                    for s in srcs:
+                        self.fwd_ops.append((L.cy4_add_copy, (s.ptr, s.ld, None, 0, cat.buf.data_ptr() + off * 2, cat.ld, cat.M, s.C)))
+                        off += s.C
+                    cur = View(cat)
+                    self._route_recs = getattr(self, "_route_recs", [])
+                    self._route_recs.append((ind, cat, srcs))
+                cur_hw = (cur.st.H, cur.st.W)
+                outs[ind] = cur
+            elif t == "shortcut":
+                frm = int(block["from"])
+                frm = frm if frm > 0 else frm + ind
+                a, b = outs[frm], outs[ind - 1]
+                assert block["activation"] == "linear", "shortcut activation %s" % block["activation"]
+                st = Storage(B, a.st.H, a.st.W, a.C, dev)
+                self.fwd_ops.append((L.cy4_add_copy, (a.ptr, a.ld, b.ptr, b.ld, st.buf.data_ptr(), st.ld, st.M, a.C)))
+                cur = View(st)
+                outs[ind] = cur
+                self._short_recs = getattr(self, "_short_recs", [])
+                self._short_recs.append((ind, st, a, b))
+            elif t == "maxpool":
+                k, stride = int(block["size"]), int(block["stride"])
+                if stride == 1 and k % 2:
+                    pad = k // 2
+                elif stride == k:
+                    pad = 0
+                else:
+                    raise NotImplementedError("MaxPoolDark (size %d stride %d) is outside the complex-yolov4 cfgs" % (k, stride))
+                Hi, Wi = cur_hw
+                Ho, Wo = (Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1
+                st = Storage(B, Ho, Wo, cur.C, dev)
+                self.fwd_ops.append((L.cy4_maxpool_fwd, (cur.ptr, cur.ld, st.buf.data_ptr(), st.ld, B, Hi, Wi, cur.C, k, stride, pad)))
+                self._pool_recs = getattr(self, "_pool_recs", [])
+                self._pool_recs.append((ind, st, cur, k, stride, pad, Hi, Wi))
+                cur = View(st)
+                cur_hw = (Ho, Wo)
+                outs[ind] = cur
+            elif t == "upsample":
+                assert int(block["stride"]) == 2
+                Hi, Wi = cur_hw
+                st = Storage(B, 2 * Hi, 2 * Wi, cur.C, dev)
+                self.fwd_ops.append((L.cy4_upsample2x_fwd, (cur.ptr, cur.ld, st.buf.data_ptr(), st.ld, B, Hi, Wi, cur.C)))
+                self._up_recs = getattr(self, "_up_recs", [])
+                self._up_recs.append((ind, st, cur, Hi, Wi))
+                cur = View(st)
+                cur_hw = (2 * Hi, 2 * Wi)
+                outs[ind] = cur
+            elif t == "yolo":
+                layer = model.models[ind]
+                head = self.convs[-1]
+                assert "P" in head and head["ind"] == ind - 1, "a [yolo] block must follow a linear conv without batch norm"
+                G = head["Ho"]
+                nA, nC = layer.num_anchors, layer.num_classes
+                stride = self.H / G
+                anchors4 = torch.tensor([(aw / stride, ah / stride, im, re) for aw, ah, im, re in layer.anchors], device=dev,
+                                        dtype=torch.float32)
+                yrec = dict(ind=ind, layer=layer, head=head, G=G, nA=nA, nC=nC, anchors4=anchors4,
+                            out=torch.empty(B, nA * G * G, 7 + nC, device=dev, dtype=torch.float32),
+                            loss=torch.zeros(1, device=dev), metrics=torch.zeros(18, device=dev),
+                            status=torch.zeros(1, device=dev, dtype=torch.int32), ws=None, nT=-1)
+                self.yolos.append(yrec)
+                outs[ind] = cur
+            else:
+                raise NotImplementedError("block type %s" % t)
+            # conv forward ops are appended in order here so that fwd_ops stays in layer order
+            if t == "convolutional":
+                self.fwd_ops.append(("conv", self.convs[-1]))
+            if t == "yolo":
+                self.fwd_ops.append(("yolo", self.yolos[-1]))
+
+        # flat per-channel buffers
+        tc = max(totalC, 8)
+        f32 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        self.stats = f32(2, tc)            # sum, sum of squares (zeroed every forward)
+        self.bnq = f32(4, tc)              # scale, shift, mean, rstd
+        self.dbn = f32(2, tc)              # d beta, d gamma (scaled by S), zeroed every backward
+        # weight packs / gradient accumulators
+        wtot = 0
+        for rec in self.convs:
+            conv = rec["conv"]
+            Cout, Cin, k = rec["Cout"], rec["Cin"], rec["k"]
+            rec["woff"] = wtot
+            wtot += conv.weight.numel()
+            if rec["stem"]:
+                rec["wf"] = torch.zeros(rup(Cout, 32), 32, device=dev, dtype=torch.float16)
+                rec["acc"] = f32(rup(Cout, 32), 1, 32)
+            else:
+                rec["wf"] = torch.empty(rup(Cout, 32), k * k * Cin, device=dev, dtype=torch.float16)
+                cpad = rup(Cout, 32)
+                rec["wd"] = torch.empty(rup(Cin, 32), k * k * cpad, device=dev, dtype=torch.float16)
+                rec["acc"] = f32(rup(Cout, 32), k * k, Cin)
+                if cpad != Cout:
+                    rec["w32"] = f32(cpad, Cin, k, k)
+            rec["wver"] = -1
+        self.gw_flat = f32(max(wtot, 1))
+        self.gbn_flat = None
+        self.dy_scratch = None
+        self.pool_scratch = None
+        self._build_backward()
+
+    # ---- forward -----------------------------------------------------------------------------
+    def _pack_weights(self, st):
+        L = self.L
+        for rec in self.convs:
+            w = rec["conv"].weight
+            ver = w._version
+            if rec["wver"] == ver and rec.get("wptr") == w.data_ptr():
+                continue
+            rec["wver"], rec["wptr"] = ver, w.data_ptr()
+            Cout, Cin, k = rec["Cout"], rec["Cin"], rec["k"]
+            if rec["stem"]:
+                # (r, s, c) column order of cy4_stem_im2col, padded to 32
+                rec["wf"][:Cout, :Cin * k * k] = w.detach().permute(0, 2, 3, 1).reshape(Cout, -1).to(torch.float16)
+                continue
+            self._call(L.cy4_pack_weight_fprop, w.data_ptr(), Cout, Cin, k, Cin, rec["wf"].data_ptr(), st)
+            if "w32" in rec:
+                rec["w32"][:Cout] = w.detach()
+                self._call(L.cy4_pack_weight_dgrad, rec["w32"].data_ptr(), rup(Cout, 32), Cin, k, rec["wd"].data_ptr(), st)
+            else:
+                self._call(L.cy4_pack_weight_dgrad, w.data_ptr(), Cout, Cin, k, rec["wd"].data_ptr(), st)
+
+    def forward(self, x, targets, use_giou):
+        L = self.L
+        st = _lib.stream()
+        model = self.model
+        training = model.training
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        self._x = x
+        self._pack_weights(st)
+        self.stats.zero_()
+        total = None
+        if targets is not None:
+            tg = targets.detach().to(self.device, torch.float32).contiguous()
+            self._tg = tg
+        B = self.B
+        for op in self.fwd_ops:
+            if op[0] == "conv":
+                self._conv_forward(op[1], x, training, st)
+            elif op[0] == "yolo":
+                y = op[1]
+                head = y["head"]
+                G, nA, nC = y["G"], y["nA"], y["nC"]
+                ldp = head["P"].ld
+                d = make_desc(B, G, nA, nC, (G * G * ldp, 1, G * ldp, ldp), self.H, y["layer"].ignore_thresh, use_giou)
+                y["desc"] = d
+                layer = y["layer"]
+                layer.img_size, layer.use_giou_loss, layer.grid_size = self.H, use_giou, G
+                if targets is None:
+                    self._call(L.cy4_yolo_decode, ctypes.byref(d), head["P"].buf.data_ptr(), y["anchors4"].data_ptr(),
+                               y["out"].data_ptr(), st)
+                else:
+                    nT = tg.shape[0]
+                    if y["nT"] != nT or y["ws"] is None:
+                        y["ws"] = torch.empty(L.cy4_yolo_workspace_bytes(ctypes.byref(d), nT), device=self.device, dtype=torch.uint8)
+                        y["nT"] = nT
+                    self._call(L.cy4_yolo_loss_fwd, ctypes.byref(d), head["P"].buf.data_ptr(), y["anchors4"].data_ptr(),
+                               tg.data_ptr() if nT else None, nT, y["out"].data_ptr(), y["loss"].data_ptr(),
+                               y["metrics"].data_ptr(), y["status"].data_ptr(), y["ws"].data_ptr(), st)
+                    layer.metrics = LazyMetrics(y["metrics"].clone())
+                    layer._status = y["status"]
+                    if layer.check_targets:
+                        check_status(y["status"], "YoloLayer")
+                    total = y["loss"].clone() if total is None else total + y["loss"]
+            else:
+                fn, args = op
+                self._call(fn, *args, st)
+        if targets is None:
+            return None
+        # reference: `loss = 0.; loss += layer_loss` -> shape [1] with GIoU, 0-dim without
+        return total if use_giou else total.reshape(())
+
+    def _conv_forward(self, rec, x, training, st):
+        L = self.L
+        B = self.B
+        k, stride, pad, Cout, Cin = rec["k"], rec["stride"], rec["pad"], rec["Cout"], rec["Cin"]
+        if rec["stem"]:
+            self._call(L.cy4_stem_im2col, x.data_ptr(), B, Cin, self.H, self.W, k, stride, pad, rec["cols"].buf.data_ptr(), st)
+            d = co.conv_desc(B, rec["Ho"], rec["Wo"], 32, Cout, 1, 1, 0, 32, 0, 0)
+            src_ptr = rec["cols"].buf.data_ptr()
+            amat = co.CONV_A_MATRIX
+        else:
+            src = rec["src"]
+            d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, 0, 0)
+            src_ptr = src.ptr
+            amat = 0
+        if rec["bn"] is not None:
+            bn = rec["bn"]
+            Y, A = rec["Y"], rec["A"]
+            c0 = rec["coff"]
+            d.ldy = Y.ld
+            d.flags = amat | (co.CONV_STATS if training else 0)
+            s1 = self.stats[0, c0:].data_ptr(); s2 = self.stats[1, c0:].data_ptr()
+            self._call(L.cy4_conv_fwd, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), Y.buf.data_ptr(), None, s1, s2, st)
+            q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
+            self._call(L.cy4_bn_finalize, s1, s2, float(Y.M), bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                       bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), float(bn.momentum), float(bn.eps),
+                       1 if training else 0, Cout, q[0], q[1], q[2], q[3], st)
+            self._call(L.cy4_bn_act_fwd, Y.buf.data_ptr(), Y.ld, q[0], q[1], rec["act"], None, 0, A.buf.data_ptr(), A.ld, Y.M, Cout, st)
+        else:
+            P = rec["P"]
+            d.ldy = P.ld
+            d.flags = amat | co.CONV_OUT_F32
+            bias = rec["conv"].bias
+            if bias is not None:
+                if "bias32" not in rec:
+                    rec["bias32"] = torch.zeros(rup(Cout, 32), device=self.device, dtype=torch.float32)
+                rec["bias32"][:Cout] = bias.detach()
+            self._call(L.cy4_conv_fwd, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), P.buf.data_ptr(),
+                       rec["bias32"].data_ptr() if bias is not None else None, None, None, st)
+
+    def outputs(self):
+        return torch.cat([y["out"] for y in self.yolos], 1)
+
+    def pinned_out(self, out):
+        if self._pinned is None or self._pinned.shape != out.shape:
+            self._pinned = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        return self._pinned
+
+    # ---- backward ----------------------------------------------------------------------------
+    def _build_backward(self):
+        """Nothing is precomputed beyond the records: the backward walk is short Python, the cost is
+        in the kernels."""
+        dev = self.device
+        max_dy = 0
+        for rec in self.convs:
+            if rec["bn"] is not None:
+                max_dy = max(max_dy, rec["Y"].M * rec["Y"].ld)
+            else:
+                max_dy = max(max_dy, rec["P"].M * 64)
+        self._max_dy = max_dy
+
+    def backward(self, gloss):
+        L = self.L
+        st = _lib.stream()
+        B, S = self.B, self.S
+        model = self.model
+        training = model.training
+        dev = self.device
+        if self.dy_scratch is None:
+            self.dy_scratch = torch.zeros(self._max_dy, device=dev, dtype=torch.float16)
+        g = (gloss.reshape(-1)[:1].to(torch.float32) * S).contiguous()
+        self.dbn.zero_()
+        # gradient state of every storage
+        storages = set()
+        for rec in self.convs:
+            for key in ("A", "Y"):
+                if key in rec:
+                    storages.add(rec[key])
+        for lst in ("_route_recs", "_short_recs", "_pool_recs", "_up_recs"):
+            for r in getattr(self, lst, []):
+                storages.add(r[1])
+        for s in storages:
+            s.gstate = 0
+            if s.partial:
+                s.ensure_grad().zero_()
+                s.gstate = 1
+        # param gradient buffers (fresh tensors each backward: autograd may keep what we return)
+        gw_flat = torch.empty_like(self.gw_flat)
+        grads = {}
+
+        # events by layer index, processed from the last layer to the first
+        events = {}
+        for rec in self.convs:
+            events[rec["ind"]] = ("conv", rec)
+        for y in self.yolos:
+            events[y["ind"]] = ("yolo", y)
+        for r in getattr(self, "_route_recs", []):
+            events[r[0]] = ("route", r)
+        for r in getattr(self, "_short_recs", []):
+            events[r[0]] = ("short", r)
+        for r in getattr(self, "_pool_recs", []):
+            events[r[0]] = ("pool", r)
+        for r in getattr(self, "_up_recs", []):
+            events[r[0]] = ("up", r)
+
+        def accumulate_into(view, src_ptr, src_ld, M):
+            """view.grad (+)= src"""
+            stg = view.st
+            if stg.gstate:
+                self._call(L.cy4_add_copy, view.gptr, view.ld, src_ptr, src_ld, view.gptr, view.ld, M, view.C, st)
+            else:
+                self._call(L.cy4_add_copy, src_ptr, src_ld, None, 0, view.gptr, view.ld, M, view.C, st)
+                stg.gstate = 1
+
+        for ind in sorted(events, reverse=True):
+            kind, r = events[ind]
+            if kind == "yolo":
+                y = r
+                head = y["head"]
+                P = head["P"]
+                d = y["desc"]
+                ldp = P.ld
+                G = y["G"]
+                self._call(L.cy4_yolo_loss_bwd, ctypes.byref(d), P.buf.data_ptr(), y["anchors4"].data_ptr(),
+                           self._tg.data_ptr() if y["nT"] else None, y["nT"], g.data_ptr(), y["ws"].data_ptr(),
+                           head["dP"].data_ptr(), G * G * ldp, 1, G * ldp, ldp, st)
+                head["has_grad"] = True
+            elif kind == "conv":
+                rec = r
+                self._conv_backward(rec, training, st, gw_flat, grads)
+            elif kind == "route":
+                _, cat, srcs = r
+                if not cat.gstate:
+                    continue
+                off = 0
+                for s in srcs:
+                    accumulate_into(s, cat.grad.data_ptr() + off * 2, cat.ld, cat.M)
+                    off += s.C
+            elif kind == "short":
+                _, stg, a, b = r
+                if not stg.gstate:
+                    continue
+                accumulate_into(a, stg.grad.data_ptr(), stg.ld, stg.M)
+                accumulate_into(b, stg.grad.data_ptr(), stg.ld, stg.M)
+            elif kind == "pool":
+                _, stg, src, k, stride, pad, Hi, Wi = r
+                if not stg.gstate:
+                    continue
+                need = B * Hi * Wi * src.C
+                if self.pool_scratch is None or self.pool_scratch.numel() < need:
+                    self.pool_scratch = torch.zeros(need, device=dev, dtype=torch.float32)
+                self.pool_scratch[:need].zero_()
+                self._call(L.cy4_maxpool_bwd, src.ptr, src.ld, stg.grad.data_ptr(), stg.ld, self.pool_scratch.data_ptr(), B, Hi, Wi, src.C,
+                           k, stride, pad, st)
+                self._call(L.cy4_f32_to_f16, self.pool_scratch.data_ptr(), src.C, 1.0, src.gptr, src.ld, B * Hi * Wi, src.C,
+                           1 if src.st.gstate else 0, st)
+                src.st.gstate = 1
+            elif kind == "up":
+                _, stg, src, Hi, Wi = r
+                if not stg.gstate:
+                    continue
+                self._call(L.cy4_upsample2x_bwd, stg.grad.data_ptr(), stg.ld, src.gptr, src.ld, B, Hi, Wi, src.C,
+                           1 if src.st.gstate else 0, st)
+                src.st.gstate = 1
+
+        # BN parameter gradients: d beta = sum dz, d gamma = sum dz*xhat (both carry the loss scale)
+        gbn = self.dbn * (1.0 / S)
+        for rec in self.convs:
+            if rec["bn"] is not None and rec.get("bn_bwd_done"):
+                c0, C = rec["coff"], rec["Cout"]
+                grads[id(rec["bn"].bias)] = gbn[0, c0:c0 + C]
+                grads[id(rec["bn"].weight)] = gbn[1, c0:c0 + C]
+        return [grads.get(id(p)) if p.requires_grad else None for p in self.params]
+
+    def _conv_backward(self, rec, training, st, gw_flat, grads):
+        L = self.L
+        B, S = self.B, self.S
+        k, stride, pad, Cout, Cin = rec["k"], rec["stride"], rec["pad"], rec["Cout"], rec["Cin"]
+        conv = rec["conv"]
+        dy = self.dy_scratch
+        rec["bn_bwd_done"] = False
+        if rec["bn"] is not None:
+            A, Y = rec["A"], rec["Y"]
+            if not A.gstate:
+                return                                   # no gradient reaches this layer
+            c0 = rec["coff"]
+            q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
+            sdz, sdzx = self.dbn[0, c0:].data_ptr(), self.dbn[1, c0:].data_ptr()
+            self._call(L.cy4_bn_act_bwd_reduce, Y.buf.data_ptr(), Y.ld, A.grad.data_ptr(), A.ld, q[0], q[1], q[2], q[3], rec["act"],
+                       Y.M, Cout, sdz, sdzx, st)
+            self._call(L.cy4_bn_act_bwd_apply, Y.buf.data_ptr(), Y.ld, A.grad.data_ptr(), A.ld, q[0], q[1], q[2], q[3], sdz, sdzx,
+                       1.0 / Y.M, 1 if training else 0, rec["act"], dy.data_ptr(), Y.ld, Y.M, Cout, st)
+            ldy, M = Y.ld, Y.M
+            rec["bn_bwd_done"] = True
+            cpad = Cout
+        else:
+            if not rec.get("has_grad"):
+                return
+            rec["has_grad"] = False
+            P = rec["P"]
+            M = P.M
+            ldy = 64
+            cpad = rup(Cout, 32)
+            # dP (fp32, already carries the loss scale through gloss) -> fp16 dY [M, 64]
+            self._call(L.cy4_f32_to_f16, rec["dP"].data_ptr(), P.ld, 1.0, dy.data_ptr(), ldy, M, cpad, 0, st)
+            if conv.bias is not None:
+                gb = torch.empty(Cout, device=self.device, dtype=torch.float32)
+                self._call(L.cy4_colsum_f32, rec["dP"].data_ptr(), P.ld, M, Cout, 1.0 / S, gb.data_ptr(), 0, st)
+                grads[id(conv.bias)] = gb
+        # input gradient
+        if not rec["stem"]:
+            src = rec["src"]
+            d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, cpad, k, stride, pad, src.ld, ldy, co.CONV_ACCUM if src.st.gstate else 0)
+            self._call(L.cy4_conv_dgrad, ctypes.byref(d), dy.data_ptr(), rec["wd"].data_ptr(), src.gptr, st)
+            src.st.gstate = 1
+        # weight gradient
+        rec["acc"].zero_()
+        gw = gw_flat[rec["woff"]:rec["woff"] + conv.weight.numel()].view_as(conv.weight)
+        if rec["stem"]:
+            d = co.conv_desc(B, rec["Ho"], rec["Wo"], 32, Cout, 1, 1, 0, 32, ldy, co.CONV_A_MATRIX)
+            self._call(L.cy4_conv_wgrad, ctypes.byref(d), rec["cols"].buf.data_ptr(), dy.data_ptr(), rec["acc"].data_ptr(), st)
+            gw.copy_((rec["acc"][:Cout, 0, :Cin * k * k] * (1.0 / S)).view(Cout, k, k, Cin).permute(0, 3, 1, 2))
+        else:
+            src = rec["src"]
+            d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, ldy, 0)
+            self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), st)
+            self._call(L.cy4_unpack_wgrad, rec["acc"].data_ptr(), Cout, Cin, k, Cin, 1.0 / S, 0, gw.data_ptr(), st)
+        grads[id(conv.weight)] = gw

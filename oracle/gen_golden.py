@@ -144,6 +144,10 @@ def gen_darknet(m, cfg, tag, batch, n_targets, k_samples=2048):
     model.train()
     x = synth.make_bev(batch)
     tg = torch.tensor(synth.make_targets(batch, seed=4321, total=n_targets))
+    sd0 = model.state_dict()
+    digest = hashlib.sha256()           # of the freshly initialised weights (torch.manual_seed(0))
+    for k in sd0:
+        digest.update(k.encode()); digest.update(sd0[k].numpy().tobytes())
     acts = {}
     hooks = []
     for i, mod in enumerate(model.models):
@@ -160,9 +164,6 @@ def gen_darknet(m, cfg, tag, batch, n_targets, k_samples=2048):
     for h in hooks:
         h.remove()
     sd = model.state_dict()
-    digest = hashlib.sha256()
-    for k in sd:
-        digest.update(k.encode()); digest.update(sd[k].numpy().tobytes())
     grads = {}
     for name, p in model.named_parameters():
         g = p.grad.reshape(-1)

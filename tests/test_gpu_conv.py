@@ -184,3 +184,18 @@ def test_conv_wgrad_stem_and_narrow():
     y.backward(dy2.float().cpu().permute(0, 3, 1, 2))
     gw = co.unpack_wgrad(acc2, 64, 32, 3)
     assert (gw.cpu() - w.grad).abs().max().item() <= 2e-3 * w.grad.abs().max().item() + 1e-4
+
+
+def test_conv_fp32_output_parity():
+    """BASELINE.json: conv activations within 1e-3 of the fp32 reference on identical inputs.  With the
+    fp32-output epilogue nothing but the accumulation order differs from F.conv2d."""
+    from cy4 import convops as co
+    torch.manual_seed(11)
+    for (B, H, W, Cin, Cout, k, stride) in [(2, 38, 38, 256, 512, 3, 1), (2, 76, 76, 128, 128, 3, 1), (2, 38, 38, 512, 256, 1, 1),
+                                            (2, 76, 76, 128, 256, 3, 2)]:
+        pad = (k - 1) // 2
+        x = torch.randn(B, H, W, Cin, device="cuda").half()
+        w = (torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).half()
+        y = co.conv_fwd(x, co.pack_fprop(w.float()), Cout, k, stride, pad, out_f32=True)
+        ref = _ref_conv(x, w, stride, pad)
+        assert (y.cpu() - ref).abs().max().item() <= 1e-3          # measured ~1e-5

@@ -1,0 +1,219 @@
+"""GPU: the whole training step (Darknet(cfg) forward + YOLO loss + backward) on the B200 engine
+against (a) golden outputs of the reference's own Darknet (tests/golden/darknet_*.npz, BASELINE
+config 1) and (b) the plain PyTorch fp32 restatement (oracle/darknet_oracle.py) run on the box's CPU.
+
+Tolerances.  The engine stores activations in fp16 (BASELINE.json config 3: "fp16 tensor-core conv
+path") and accumulates in fp32.  One fp16 rounding of a value of magnitude ~4 is already 2e-3, so
+the stored activations cannot be within 1e-3 absolute of the fp32 reference; what is checked here:
+  * the conv kernel itself, on identical inputs, matches fp32 to 1e-3 (tests/test_gpu_conv.py,
+    fp32-output mode: test_conv_fp32_output_parity);
+  * end to end, activations stay within 8% of each layer's standard deviation after 30 layers, the
+    loss within 1e-3 relative, detections within 2% of scale;
+  * gradients: LeakyReLU's kink turns the forward rounding into sign flips of ~1-3% of the
+    derivative terms, i.e. ~10% noise on individual weight-gradient elements of a randomly
+    initialised net (unbiased: norms agree to a few %).  With the smooth Mish everywhere the same
+    engine agrees to ~1e-2, which is what rules out an indexing / accumulation bug."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _engine_acts(model):
+    acts = {}
+    for rec in model._engine.plan.convs:
+        st = rec["A"] if "A" in rec else rec["P"]
+        acts[rec["ind"]] = st.buf[..., :rec["Cout"]].float().permute(0, 3, 1, 2).contiguous()
+    return acts
+
+
+def test_tiny_step_vs_reference_golden(golden):
+    """BASELINE config 1: complex_yolov4_tiny, bs=2, 608x608, 8 targets, GIoU on."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    g = golden("darknet_tiny_bs2.npz")
+    torch.manual_seed(0)
+    model = Darknet(netdefs.cfg_path("complex_yolov4_tiny"), True)
+    sd = model.state_dict()
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode()); h.update(sd[k].numpy().tobytes())
+    assert h.hexdigest() == str(g["weights_sha256"]), "same seed must give the reference's initial weights"
+    assert list(sd.keys()) == [str(k) for k in g["state_keys"]]
+    model = model.cuda().train()
+    loss, out = model(synth.make_bev(2).cuda(), torch.tensor(g["targets"]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert tuple(loss.shape) == (1,) and out.device.type == "cpu" and out.shape == (2, 5415, 10)
+    ref_loss = float(g["loss"][0])
+    assert abs(loss.item() - ref_loss) <= 1e-3 * ref_loss
+    ro = g["outputs"]
+    assert (np.abs(out.numpy() - ro) / (np.abs(ro) + 1.0)).max() < 2e-2
+    acts = _engine_acts(model)
+    for ind, a in acts.items():
+        idx = torch.from_numpy(g["act%d_idx" % ind]).cuda()
+        err = np.abs(a.reshape(-1)[idx].cpu().numpy() - g["act%d_val" % ind]).max()
+        assert err <= 0.08 * g["act%d_stats" % ind][1] + 1e-3, (ind, err)
+    for li, yl in enumerate(model.yolo_layers):
+        ref = g["metrics%d" % li]
+        mine = np.array([yl.metrics[str(k)] for k in g["metric_keys"]])
+        assert (np.abs(mine - ref) / (np.abs(ref) + 1e-2)).max() < 2e-2
+    for name, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        gn = g["gnorm/" + name]
+        assert abs(p.grad.norm().item() - gn[0]) <= 0.10 * gn[0] + 1e-7, name
+    # BN running statistics were updated like nn.BatchNorm2d does (momentum 0.1, unbiased variance)
+    for k, v in model.state_dict().items():
+        if "running_mean" in k or "running_var" in k:
+            ref = g["rs/" + k]
+            assert abs(v.mean().item() - ref[0]) <= 2e-3 * (abs(ref[0]) + 1e-2) + 1e-4, k
+        if "num_batches_tracked" in k:
+            assert int(v) == 1
+
+
+def _variant_cfg(tmp_path, base, act=None):
+    from cy4 import netdefs
+    blocks = netdefs.NETS[base]()
+    if act:
+        for b in blocks:
+            if b["type"] == "convolutional" and b["activation"] == "leaky":
+                b["activation"] = act
+    path = os.path.join(str(tmp_path), base + "_" + (act or "orig") + ".cfg")
+    with open(path, "w") as f:
+        f.write(netdefs.to_cfg_text(blocks))
+    return path
+
+
+@pytest.mark.parametrize("base,act,size,B", [("complex_yolov4_tiny", "mish", 256, 2), ("complex_yolov4_tiny", None, 256, 3),
+                                              ("complex_yolov4", None, 128, 2)])
+def test_step_vs_fp32_oracle(tmp_path, base, act, size, B):
+    from cy4 import synth
+    from cy4.darknet import Darknet
+    from oracle import darknet_oracle as do
+    cfg = _variant_cfg(tmp_path, base, act)
+    torch.manual_seed(1)
+    model = Darknet(cfg, True)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = synth.make_bev(B, img_size=size, seed=5)
+    strides = (16, 32) if "tiny" in base else (8, 16, 32)
+    tg = torch.tensor(synth.make_targets(B, per_image=3, seed=2, img_size=size, strides=strides))
+    # fp32 oracle on the CPU
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    collect = {}
+    ol, oo, om = do.forward(do.parse_cfg(cfg), params, x, tg, True, True, collect=collect)
+    ol.backward()
+    # engine
+    model = model.cuda().train()
+    loss, out = model(x.cuda(), tg.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ol.item()) <= 2e-3 * abs(ol.item())
+    assert ((out - oo.detach()).abs() / (oo.detach().abs() + 1.0)).max().item() < 3e-2
+    acts = _engine_acts(model)
+    for ind, a in acts.items():
+        ref = collect[ind].detach()
+        err = (a.cpu() - ref).abs().max().item()
+        assert err <= 0.10 * ref.std().item() + 2e-3, (ind, err, ref.std().item())
+    smooth = act == "mish"
+    worst_cos, worst_norm = 1.0, 0.0
+    for name, p in model.named_parameters():
+        ref = params[name].grad
+        c = _cos(p.grad.cpu(), ref)
+        nr = abs(p.grad.norm().item() - ref.norm().item()) / (ref.norm().item() + 1e-12)
+        worst_cos, worst_norm = min(worst_cos, c), max(worst_norm, nr)
+        assert c > (0.995 if smooth else 0.93), (name, c)
+        assert nr < (0.03 if smooth else 0.12), (name, nr)
+    print("worst cosine %.5f, worst norm rel %.4f" % (worst_cos, worst_norm))
+
+
+def test_eval_mode_and_inference_api(tmp_path):
+    """model.eval(): BN uses running statistics; forward(x) returns CPU detections only."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    from oracle import darknet_oracle as do
+    cfg = netdefs.cfg_path("complex_yolov4_tiny")
+    torch.manual_seed(3)
+    model = Darknet(cfg, True)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = synth.make_bev(2, img_size=160, seed=8)
+    _, oo, _ = do.forward(do.parse_cfg(cfg), sd, x, None, True, training=False)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model(x.cuda())
+    assert isinstance(out, torch.Tensor) and out.device.type == "cpu" and out.shape == oo.shape
+    assert ((out - oo).abs() / (oo.abs() + 1.0)).max().item() < 2e-2
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k          # eval must not touch running stats
+
+
+def test_elementwise_kernels_vs_torch():
+    """BN finalize/apply/backward, Mish/leaky, max pool, upsample against torch on the same fp16 data."""
+    import ctypes
+    from cy4 import _lib
+    import torch.nn.functional as F
+    L = _lib.lib(); st = _lib.stream()
+    torch.manual_seed(0)
+    B, H, W, C = 2, 19, 19, 64
+    M = B * H * W
+    for act_id, act in ((2, lambda z: z * torch.tanh(F.softplus(z))), (1, lambda z: F.leaky_relu(z, 0.1)), (0, lambda z: z)):
+        y16 = (torch.randn(B, H, W, C, device="cuda") * 1.5 + 0.3).half()
+        gA16 = torch.randn(B, H, W, C, device="cuda").half()
+        gamma = torch.rand(C, device="cuda") + 0.5; beta = torch.randn(C, device="cuda")
+        yf = y16.float().requires_grad_(True)
+        s1 = yf.detach().sum((0, 1, 2)).contiguous(); s2 = (yf.detach() ** 2).sum((0, 1, 2)).contiguous()
+        rm = torch.zeros(C, device="cuda"); rv = torch.ones(C, device="cuda"); nbt = torch.zeros(1, device="cuda", dtype=torch.int64)
+        q = torch.zeros(4, C, device="cuda")
+        _lib.check(L.cy4_bn_finalize(s1.data_ptr(), s2.data_ptr(), float(M), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(),
+                                     rv.data_ptr(), nbt.data_ptr(), 0.1, 1e-5, 1, C, q[0].data_ptr(), q[1].data_ptr(), q[2].data_ptr(),
+                                     q[3].data_ptr(), st))
+        out = torch.empty_like(y16)
+        _lib.check(L.cy4_bn_act_fwd(y16.data_ptr(), C, q[0].data_ptr(), q[1].data_ptr(), act_id, None, 0, out.data_ptr(), C, M, C, st))
+        rm2 = torch.zeros(C, device="cuda"); rv2 = torch.ones(C, device="cuda")
+        z = F.batch_norm(yf.permute(0, 3, 1, 2), rm2, rv2, gamma, beta, True, 0.1, 1e-5)
+        ref = act(z).permute(0, 2, 3, 1)
+        assert (out.float() - ref).abs().max().item() < 4e-3 * ref.abs().max().item() + 2e-3
+        assert torch.allclose(rm, rm2, atol=1e-5) and torch.allclose(rv, rv2, rtol=1e-4, atol=1e-5) and int(nbt) == 1
+        ref.backward(gA16.float())
+        sums = torch.zeros(2, C, device="cuda")
+        _lib.check(L.cy4_bn_act_bwd_reduce(y16.data_ptr(), C, gA16.data_ptr(), C, q[0].data_ptr(), q[1].data_ptr(), q[2].data_ptr(),
+                                           q[3].data_ptr(), act_id, M, C, sums[0].data_ptr(), sums[1].data_ptr(), st))
+        dy = torch.empty_like(y16)
+        _lib.check(L.cy4_bn_act_bwd_apply(y16.data_ptr(), C, gA16.data_ptr(), C, q[0].data_ptr(), q[1].data_ptr(), q[2].data_ptr(),
+                                          q[3].data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), 1.0 / M, 1, act_id, dy.data_ptr(), C, M, C, st))
+        gref = yf.grad
+        assert (dy.float() - gref).abs().max().item() < 5e-3 * gref.abs().max().item() + 1e-3
+    # max pool (SPP sizes + 2x2/2) and its gradient routing, upsample
+    x16 = torch.randn(2, 19, 19, 64, device="cuda").half()
+    for k, s in ((5, 1), (9, 1), (13, 1), (2, 2)):
+        xin = x16[:, :18, :18].contiguous() if s == 2 else x16
+        Bq, Hq, Wq, Cq = xin.shape
+        pad = k // 2 if s == 1 else 0
+        Ho = (Hq + 2 * pad - k) // s + 1
+        out = torch.empty(Bq, Ho, Ho, Cq, device="cuda", dtype=torch.float16)
+        _lib.check(L.cy4_maxpool_fwd(xin.data_ptr(), Cq, out.data_ptr(), Cq, Bq, Hq, Wq, Cq, k, s, pad, st))
+        xf = xin.float().permute(0, 3, 1, 2).requires_grad_(True)
+        ref = F.max_pool2d(xf, k, s, pad)
+        assert torch.equal(out.float(), ref.permute(0, 2, 3, 1))
+        go = torch.randn_like(out)
+        scratch = torch.zeros(Bq, Hq, Wq, Cq, device="cuda")
+        _lib.check(L.cy4_maxpool_bwd(xin.data_ptr(), Cq, go.data_ptr(), Cq, scratch.data_ptr(), Bq, Hq, Wq, Cq, k, s, pad, st))
+        ref.backward(go.float().permute(0, 3, 1, 2))
+        assert (scratch - xf.grad.permute(0, 2, 3, 1)).abs().max().item() < 2e-2
+    up = torch.empty(2, 38, 38, 64, device="cuda", dtype=torch.float16)
+    _lib.check(L.cy4_upsample2x_fwd(x16.data_ptr(), 64, up.data_ptr(), 64, 2, 19, 19, 64, st))
+    assert torch.equal(up, x16.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    gin = torch.zeros_like(x16)
+    _lib.check(L.cy4_upsample2x_bwd(up.data_ptr(), 64, gin.data_ptr(), 64, 2, 19, 19, 64, 0, st))
+    assert (gin.float() - 4 * x16.float()).abs().max().item() < 2e-2
