@@ -1,4 +1,5 @@
 // api_common.cu -- version / error / device entry points of the C-ABI.
+#include <atomic>
 #include <cstdarg>
 
 #include "common.cuh"
@@ -14,6 +15,9 @@ void set_error(const char *fmt, ...)
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count()
 {
@@ -35,6 +39,11 @@ extern "C" {
 int cy4_version(void) { return CY4_VERSION; }
 
 const char *cy4_last_error(void) { return cy4::g_err; }
+
+long long cy4_kernel_launches(int reset)
+{
+    return reset ? cy4::g_launches.exchange(0) : cy4::g_launches.load();
+}
 
 int cy4_device_ok(void)
 {

@@ -12,6 +12,7 @@ namespace cy4 {
 
 void set_error(const char *fmt, ...);   // thread-local message, returned by cy4_last_error()
 int sm_count();                         // SM count of the current device (cached per device)
+void count_launches(int n);             // bookkeeping behind cy4_kernel_launches()
 
 }  // namespace cy4
 
@@ -33,8 +34,9 @@ int sm_count();                         // SM count of the current device (cache
     } while (0)
 
 // Launch-time errors only (no synchronisation).
-static inline int cy4_launch_status(const char *what)
+static inline int cy4_launch_status(const char *what, int n_kernels = 1)
 {
+    cy4::count_launches(n_kernels);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         cy4::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));

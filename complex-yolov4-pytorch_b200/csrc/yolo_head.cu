@@ -475,7 +475,7 @@ int cy4_yolo_loss_fwd(const cy4_yolo_desc *d, const float *pred, const float *an
     const int a_fast = d->sC < d->sW ? 1 : 0;
     yolo_dense_kernel<true><<<grid, kDenseBlock, 0, st>>>(*d, hv, anchors4, ws, output, a_fast);
     yolo_finalize_kernel<<<1, 64, 0, st>>>(*d, ws, grid, nT, loss, metrics);
-    return cy4_launch_status("cy4_yolo_loss_fwd");
+    return cy4_launch_status("cy4_yolo_loss_fwd", nT > 0 ? 3 : 2);
 }
 
 int cy4_yolo_loss_bwd(const cy4_yolo_desc *d, const float *pred, const float *anchors4, const float *targets8, int64_t nT,
@@ -494,7 +494,7 @@ int cy4_yolo_loss_bwd(const cy4_yolo_desc *d, const float *pred, const float *an
     yolo_dense_bwd_kernel<<<dense_grid(cells), kDenseBlock, 0, st>>>(*d, hv, ws, gloss, dpred, dsB, dsC, dsH, dsW, a_fast);
     if (nT > 0 && d->use_giou)
         yolo_targets_bwd_kernel<<<(unsigned)((nT + 127) / 128), 128, 0, st>>>(*d, hv, anchors4, ws, nT, gloss, dpred, dsB, dsC, dsH, dsW);
-    return cy4_launch_status("cy4_yolo_loss_bwd");
+    return cy4_launch_status("cy4_yolo_loss_bwd", (nT > 0 && d->use_giou) ? 2 : 1);
 }
 
 int cy4_build_targets(const cy4_yolo_desc *d, const float *pred_boxes, const float *pred_cls, const float *targets8,
@@ -520,7 +520,7 @@ int cy4_build_targets(const cy4_yolo_desc *d, const float *pred_boxes, const flo
     build_targets_dense_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(*d, ws, iou_scores, class_mask, obj_mask, noobj_mask,
                                                                               tx, ty, tw, th, tim, tre, tcls, tconf);
     build_targets_misc_kernel<<<(unsigned)std::max<int64_t>(1, (nT + 127) / 128), 128, 0, st>>>(ws, nT, giou_loss, idx);
-    return cy4_launch_status("cy4_build_targets");
+    return cy4_launch_status("cy4_build_targets", nT > 0 ? 3 : 2);
 }
 
 }  // extern "C"

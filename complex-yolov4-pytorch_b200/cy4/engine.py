@@ -25,6 +25,7 @@ from . import convops as co
 from .yolo import LazyMetrics, make_desc, check_status
 
 ACT = {"linear": 0, "leaky": 1, "mish": 2}
+_PROFILED = ("cy4_conv_fwd", "cy4_conv_dgrad", "cy4_conv_wgrad")
 
 
 def rup(x, m):
@@ -148,11 +149,22 @@ class Plan:
         self.fwd_ops, self.bwd_ops = [], []
         self.params = None
         self._pinned = None
+        self.prof = None             # list -> CUDA-event timing of every conv launch (bench.py roofline pass)
         self._build()
 
     # ---- helpers -----------------------------------------------------------------------------
     def _call(self, fn, *args):
-        rc = fn(*args)
+        prof = self.prof
+        if prof is not None and fn.__name__ in _PROFILED:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            d = args[0]._obj
+            prof.append((fn.__name__, e0, e1, 2.0 * d.B * d.Ho * d.Wo * d.Cout * d.ksize * d.ksize * d.Cin,
+                         (d.Cin, d.Cout, d.ksize, d.stride, d.Ho)))
+        else:
+            rc = fn(*args)
         if rc < 0:
             _lib.check(rc, fn.__name__)
 

@@ -40,6 +40,8 @@ CY4_API int cy4_version(void);
 CY4_API const char *cy4_last_error(void);
 /* 0 if a CUDA device of compute capability 10.x is usable by this library, <0 otherwise (host call). */
 CY4_API int cy4_device_ok(void);
+/* number of CUDA kernels this library has launched in this process (reset != 0: return and clear) */
+CY4_API long long cy4_kernel_launches(int reset);
 
 /* ---- rotated-box geometry -------------------------------------------------------------------
  * utils/iou_rotated_boxes_utils.py:98-142  iou_pred_vs_target_boxes (element-wise pairs), with
