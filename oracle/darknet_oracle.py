@@ -35,9 +35,22 @@ def parse_cfg(path):
     return blocks
 
 
-def forward(blocks, sd, x, targets=None, use_giou=True, training=True, collect=None, update_running=False):
+def _r16(t):
+    """Round to fp16 storage precision with a straight-through gradient."""
+    return t + (t.detach().half().float() - t.detach())
+
+
+def forward(blocks, sd, x, targets=None, use_giou=True, training=True, collect=None, update_running=False, storage="fp32"):
     """sd: state_dict-like mapping (tensors may require grad).  Returns (loss|None, outputs [B,N,10],
-    per-yolo metrics list).  `collect` (dict) receives every conv block's activated output."""
+    per-yolo metrics list).  `collect` (dict) receives every conv block's activated output.
+
+    storage="fp16" restates the SAME math at the engine's documented storage precision:
+    conv inputs and weights rounded to fp16, fp32 accumulation, BatchNorm statistics from the fp32
+    conv result, the raw conv output and the activated output each rounded once to fp16 (fp32 for the
+    linear head convs), straight-through gradients.  It isolates implementation errors from the
+    ~1e-2..1 relative drift that fp16 rounding alone produces in a randomly initialised 160-layer
+    network (chaotic amplification, measured in tests/golden/darknet_*_emu16.npz)."""
+    emu = storage == "fp16"
     outs, yolo_out, metrics = {}, [], []
     loss = 0.
     img = x.shape[2]
@@ -53,17 +66,35 @@ def forward(blocks, sd, x, targets=None, use_giou=True, training=True, collect=N
             pad = (k - 1) // 2 if int(b["pad"]) else 0
             pre = "models.%d." % ind
             bn = int(b["batch_normalize"])
-            x = F.conv2d(x, sd[pre + "conv%d.weight" % conv_id], None if bn else sd[pre + "conv%d.bias" % conv_id], s, pad)
+            w = sd[pre + "conv%d.weight" % conv_id]
+            if emu:
+                w = _r16(w)
+                x = _r16(x)
+            x = F.conv2d(x, w, None if bn else sd[pre + "conv%d.bias" % conv_id], s, pad)
             if bn:
                 rm, rv = sd[pre + "bn%d.running_mean" % conv_id], sd[pre + "bn%d.running_var" % conv_id]
                 if not update_running:
                     rm, rv = rm.clone(), rv.clone()
-                x = F.batch_norm(x, rm, rv, sd[pre + "bn%d.weight" % conv_id], sd[pre + "bn%d.bias" % conv_id], training, 0.1, 1e-5)
+                gamma, beta = sd[pre + "bn%d.weight" % conv_id], sd[pre + "bn%d.bias" % conv_id]
+                if emu and training:
+                    # statistics from the fp32 conv result, normalisation applied to the fp16-stored one
+                    mean = x.mean((0, 2, 3)); var = x.var((0, 2, 3), unbiased=False)
+                    n = x.numel() / x.shape[1]
+                    with torch.no_grad():
+                        rm.mul_(0.9).add_(0.1 * mean); rv.mul_(0.9).add_(0.1 * var * n / max(n - 1, 1))
+                    sc = gamma / torch.sqrt(var + 1e-5)
+                    x = _r16(x) * sc.view(1, -1, 1, 1) + (beta - mean * sc).view(1, -1, 1, 1)
+                else:
+                    if emu:
+                        x = _r16(x)
+                    x = F.batch_norm(x, rm, rv, gamma, beta, training, 0.1, 1e-5)
             a = b["activation"]
             if a == "leaky":
                 x = F.leaky_relu(x, 0.1)
             elif a == "mish":
                 x = x * torch.tanh(F.softplus(x))
+            if emu and bn:
+                x = _r16(x)
             if collect is not None:
                 collect[ind] = x
         elif t == "route":

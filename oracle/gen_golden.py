@@ -185,16 +185,55 @@ def gen_darknet(m, cfg, tag, batch, n_targets, k_samples=2048):
          metric_keys=np.array(list(model.yolo_layers[0].metrics.keys())), **acts, **grads, **mets, **rs)
 
 
+def gen_darknet_emu16(cfg, tag, batch, n_targets, k_samples=2048):
+    """Same step through oracle/darknet_oracle.py at fp16 storage precision (no reference code involved):
+    separates implementation errors from fp16 drift.  Same seeds / sample indices as gen_darknet."""
+    from oracle import darknet_oracle as do
+    from cy4 import netdefs
+    from cy4.darknet import Darknet
+    path = netdefs.cfg_path(cfg.replace(".cfg", ""))
+    torch.manual_seed(0)
+    sd = Darknet(path, True).state_dict()
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    x = synth.make_bev(batch)
+    tg = torch.tensor(synth.make_targets(batch, seed=4321, total=n_targets))
+    collect = {}
+    loss, outputs, mets = do.forward(do.parse_cfg(path), params, x, tg, True, True, collect=collect, storage="fp16")
+    loss.backward()
+    acts, grads = {}, {}
+    for i, a in collect.items():
+        flat = a.detach().reshape(-1)
+        sel = _sample_idx(flat.numel(), k_samples, 1000 + i)
+        acts[f"act{i}_idx"] = sel
+        acts[f"act{i}_val"] = flat[torch.from_numpy(sel)].numpy().copy()
+        acts[f"act{i}_stats"] = np.array([flat.mean().item(), flat.std().item(), flat.abs().max().item()], np.float64)
+    for name, p in params.items():
+        if p.grad is None:
+            continue
+        g = p.grad.reshape(-1)
+        grads["gnorm/" + name] = np.array([g.norm().item(), g.abs().max().item()], np.float64)
+        sel = _sample_idx(g.numel(), 4096, 7)
+        grads["gidx/" + name] = sel
+        grads["gval/" + name] = g[torch.from_numpy(sel)].numpy().copy()
+    mk = list(mets[0].keys())
+    save(f"darknet_{tag}_emu16.npz", cfg=cfg, batch=batch, targets=tg.numpy(), loss=loss.detach().numpy(),
+         outputs=outputs.detach().numpy(), metric_keys=np.array(mk),
+         **{f"metrics{i}": np.array([m[k] for k in mk], np.float64) for i, m in enumerate(mets)}, **acts, **grads)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     m = rl.load()
-    which = sys.argv[1:] or ["pairs", "anchor", "yolo", "tiny", "v4"]
+    which = sys.argv[1:] or ["pairs", "anchor", "yolo", "tiny", "v4", "emu"]
     if "pairs" in which: gen_pairs(m)
     if "anchor" in which: gen_anchor_iou(m)
     if "yolo" in which: gen_yolo_layer(m)
     if "tiny" in which: gen_darknet(m, "complex_yolov4_tiny.cfg", "tiny_bs2", 2, 8)       # BASELINE config 1
     if "v4" in which: gen_darknet(m, "complex_yolov4.cfg", "v4_bs2", 2, 8)
+    if "emu" in which:
+        gen_darknet_emu16("complex_yolov4_tiny.cfg", "tiny_bs2", 2, 8)
+        gen_darknet_emu16("complex_yolov4.cfg", "v4_bs2", 2, 8)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,98 @@
+"""CPU: the drop-in import root exposes the reference's module / symbol names."""
+import importlib
+import sys
+
+from conftest import PKG
+
+
+def test_module_names_and_symbols():
+    assert PKG in sys.path
+    for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")]:
+        del sys.modules[k]
+    d2p = importlib.import_module("models.darknet2pytorch")
+    for name in ("Darknet", "Mish", "MaxPoolDark", "Upsample_expand", "Reorg", "GlobalAvgPool2d", "EmptyModule"):
+        assert hasattr(d2p, name), name
+    yl = importlib.import_module("models.yolo_layer")
+    assert hasattr(yl, "YoloLayer")
+    mu = importlib.import_module("models.model_utils")
+    for name in ("create_model", "get_num_parameters", "make_data_parallel"):
+        assert hasattr(mu, name)
+    du = importlib.import_module("models.darknet_utils")
+    for name in du.__all__:
+        assert hasattr(du, name), name
+    iou = importlib.import_module("utils.iou_rotated_boxes_utils")
+    for name in ("get_polygons_areas_fix_xy", "iou_rotated_boxes_targets_vs_anchors", "iou_pred_vs_target_boxes",
+                 "get_corners_vectorize", "cvt_box_2_polygon"):
+        assert hasattr(iou, name), name
+    cal = importlib.import_module("utils.cal_intersection_rotated_boxes")
+    for name in ("intersection_area", "PolyArea2D", "Line"):
+        assert hasattr(cal, name), name
+    tu = importlib.import_module("utils.torch_utils")
+    assert set(tu.__all__) == {"convert2cpu", "convert2cpu_long", "to_cpu"}
+
+
+def test_state_dict_and_optimizer_groups():
+    """Checkpoint / optimizer contract: 648 state entries for v4 with the reference's key names;
+    create_optimizer's substring grouping gives 110 conv weights / 110 biases / 107 bn weights."""
+    import torch
+    from cy4 import netdefs
+    from cy4.darknet import Darknet
+    m = Darknet(netdefs.cfg_path("complex_yolov4"), True)
+    sd = m.state_dict()
+    assert len(sd) == 648 and len(m.models) == 162
+    assert "models.0.conv1.weight" in sd and "models.0.bn1.running_var" in sd and "models.138.conv94.bias" in sd
+    assert sum(p.numel() for p in m.parameters()) == 63959226
+    pg0 = pg1 = pg2 = 0
+    for k, v in m.named_parameters():
+        if ".bias" in k:
+            pg2 += 1
+        elif "conv" in k and ".weight" in k:
+            pg1 += 1
+        else:
+            pg0 += 1
+    assert (pg1, pg2, pg0) == (110, 110, 107)
+    t = Darknet(netdefs.cfg_path("complex_yolov4_tiny"), True)
+    assert sum(p.numel() for p in t.parameters()) == 5883356
+    assert [type(l).__name__ for l in t.yolo_layers] == ["YoloLayer", "YoloLayer"]
+    assert t.width == 416 and m.width == 608 and m.num_classes == 3
+    assert isinstance(m.header, torch.Tensor) and m.seen == 0
+
+
+def test_cfg_grammar(tmp_path):
+    from cy4.darknet import parse_cfg
+    p = tmp_path / "a.cfg"
+    p.write_text("[net]\n# comment\nwidth=32\nheight = 32\nchannels=3\n\n[convolutional]\nfilters=8\nsize=3\nstride=1\npad=1\nactivation=leaky\n"
+                 "[cost]\ntype=sse\n")
+    b = parse_cfg(str(p))
+    assert b[0]["type"] == "net" and b[0]["height"] == "32"
+    assert b[1]["batch_normalize"] == 0 and b[1]["filters"] == "8"
+    assert b[2]["_type"] == "sse"
+
+
+def test_netdefs_match_reference_cfgs():
+    """Block-for-block equality with the reference cfg files (build container only)."""
+    import os
+    import pytest
+    from cy4 import netdefs
+    from cy4.darknet import parse_cfg
+    ref_dir = "/root/reference/src/config/cfg"
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not present")
+    keys = {"convolutional": ["batch_normalize", "filters", "size", "stride", "pad", "activation"], "route": ["layers", "groups", "group_id"],
+            "shortcut": ["from", "activation"], "maxpool": ["size", "stride"], "upsample": ["stride"],
+            "yolo": ["mask", "anchors", "classes", "scale_x_y", "ignore_thresh"], "net": ["width", "height", "channels"]}
+    for name in netdefs.NETS:
+        ref = parse_cfg(os.path.join(ref_dir, name + ".cfg"))
+        mine = parse_cfg(netdefs.cfg_path(name))
+        assert len(ref) == len(mine)
+        for a, b in zip(ref, mine):
+            assert a["type"] == b["type"]
+            for k in keys[a["type"]]:
+                va, vb = a.get(k), b.get(k)
+                if k in ("layers", "mask", "anchors") and va is not None:
+                    va, vb = va.replace(" ", ""), vb.replace(" ", "")
+                if k in ("scale_x_y", "ignore_thresh"):
+                    va, vb = float(va), float(vb)
+                if k == "batch_normalize":
+                    va, vb = int(va), int(vb)
+                assert va == vb, (name, k, va, vb)

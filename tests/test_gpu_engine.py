@@ -58,22 +58,34 @@ def test_step_vs_reference_golden(golden, tag, cfgname, nout):
     assert tuple(loss.shape) == (1,) and out.device.type == "cpu" and out.shape == (2, nout, 10)
     ref_loss = float(g["loss"][0])
     print(tag, "loss", loss.item(), "reference", ref_loss)
-    assert abs(loss.item() - ref_loss) <= 2e-3 * ref_loss
-    ro = g["outputs"]
-    assert (np.abs(out.numpy() - ro) / (np.abs(ro) + 1.0)).max() < 2e-2
+    deep = tag.startswith("v4")
+    # fp16 storage drift vs the fp32 reference: small for the 21-conv tiny net; in the randomly
+    # initialised 110-conv net the same rounding is amplified layer by layer until the head
+    # activations decorrelate (the fp16-emulating oracle shows the identical profile, see
+    # test_step_vs_fp16_storage_oracle), so only the loss (a statistic) is compared there.
+    assert abs(loss.item() - ref_loss) <= (2e-2 if deep else 2e-3) * ref_loss
     acts = _engine_acts(model)
-    for ind, a in acts.items():
-        idx = torch.from_numpy(g["act%d_idx" % ind]).cuda()
-        err = np.abs(a.reshape(-1)[idx].cpu().numpy() - g["act%d_val" % ind]).max()
-        assert err <= 0.08 * g["act%d_stats" % ind][1] + 1e-3, (ind, err)
-    for li, yl in enumerate(model.yolo_layers):
-        ref = g["metrics%d" % li]
-        mine = np.array([yl.metrics[str(k)] for k in g["metric_keys"]])
-        assert (np.abs(mine - ref) / (np.abs(ref) + 1e-2)).max() < 2e-2
+    if not deep:
+        ro = g["outputs"]
+        assert (np.abs(out.numpy() - ro) / (np.abs(ro) + 1.0)).max() < 2e-2
+        for ind, a in acts.items():
+            idx = torch.from_numpy(g["act%d_idx" % ind]).cuda()
+            err = np.abs(a.reshape(-1)[idx].cpu().numpy() - g["act%d_val" % ind]).max()
+            assert err <= 0.08 * g["act%d_stats" % ind][1] + 1e-3, (ind, err)
+        for li, yl in enumerate(model.yolo_layers):
+            ref = g["metrics%d" % li]
+            mine = np.array([yl.metrics[str(k)] for k in g["metric_keys"]])
+            assert (np.abs(mine - ref) / (np.abs(ref) + 1e-2)).max() < 2e-2
+    else:
+        for ind in sorted(acts)[:12]:        # the first dozen layers are still in the linear regime
+            idx = torch.from_numpy(g["act%d_idx" % ind]).cuda()
+            err = np.abs(acts[ind].reshape(-1)[idx].cpu().numpy() - g["act%d_val" % ind]).max()
+            assert err <= 0.03 * g["act%d_stats" % ind][1] + 1e-3, (ind, err)
     for name, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
         gn = g["gnorm/" + name]
-        assert abs(p.grad.norm().item() - gn[0]) <= 0.10 * gn[0] + 1e-7, name
+        if not deep:
+            assert abs(p.grad.norm().item() - gn[0]) <= 0.10 * gn[0] + 1e-7, name
     # BN running statistics were updated like nn.BatchNorm2d does (momentum 0.1, unbiased variance)
     for k, v in model.state_dict().items():
         if "running_mean" in k or "running_var" in k:
@@ -81,6 +93,42 @@ def test_step_vs_reference_golden(golden, tag, cfgname, nout):
             assert abs(v.mean().item() - ref[0]) <= 2e-3 * (abs(ref[0]) + 1e-2) + 1e-4, k
         if "num_batches_tracked" in k:
             assert int(v) == 1
+
+
+@pytest.mark.parametrize("tag,cfgname", [("tiny_bs2", "complex_yolov4_tiny"), ("v4_bs2", "complex_yolov4")])
+def test_step_vs_fp16_storage_oracle(golden, tag, cfgname):
+    """Same step against the oracle restated at the engine's storage precision (fp16 activations and
+    weights, fp32 accumulation / statistics; oracle/darknet_oracle.py storage="fp16"): with the rounding
+    points aligned, what remains is accumulation order, so the agreement must be tight in EVERY layer
+    of both networks -- this is the test that catches indexing / layout / accumulation bugs."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    g = golden("darknet_%s_emu16.npz" % tag)
+    torch.manual_seed(0)
+    model = Darknet(netdefs.cfg_path(cfgname), True).cuda().train()
+    loss, out = model(synth.make_bev(2).cuda(), torch.tensor(g["targets"]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss = float(g["loss"][0])
+    worst_act = 0.0
+    acts = _engine_acts(model)
+    for ind, a in acts.items():
+        idx = torch.from_numpy(g["act%d_idx" % ind]).cuda()
+        err = np.abs(a.reshape(-1)[idx].cpu().numpy() - g["act%d_val" % ind]).max()
+        worst_act = max(worst_act, err / g["act%d_stats" % ind][1])
+    worst_cos, worst_norm = 1.0, 0.0
+    for name, p in model.named_parameters():
+        idx = torch.from_numpy(g["gidx/" + name]).cuda()
+        got = p.grad.reshape(-1)[idx].cpu()
+        ref = torch.from_numpy(g["gval/" + name])
+        gn = g["gnorm/" + name]
+        worst_cos = min(worst_cos, _cos(got, ref))
+        worst_norm = max(worst_norm, abs(p.grad.norm().item() - gn[0]) / (gn[0] + 1e-12))
+    print(tag, "loss", loss.item(), "emu16 oracle", ref_loss, "worst act err/std", worst_act, "worst grad cos", worst_cos,
+          "worst grad-norm rel", worst_norm)
+    assert abs(loss.item() - ref_loss) <= 2e-3 * ref_loss
+    assert worst_act <= 0.05
+    assert worst_cos >= 0.98 and worst_norm <= 0.05
 
 
 def _variant_cfg(tmp_path, base, act=None):
