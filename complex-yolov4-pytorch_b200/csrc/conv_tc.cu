@@ -30,7 +30,8 @@ constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr int kAStageBytes = kBlockM * 128;        // 16 KB (kchunk 64) ; 8 KB used when kchunk 32
 constexpr int kBStageBytes = 256 * 128;            // 32 KB (block_n 256, kchunk 64)
-constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kMaxStatCh = 1024;                   // per-CTA shared accumulators for the BN statistics
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/ + 2 * kMaxStatCh * 4;
 constexpr uint32_t kTmemCols = 512;
 
 struct SmemCtl {
@@ -46,6 +47,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t *sA = smem;
     uint8_t *sB = smem + kStages * kAStageBytes;
     SmemCtl *ctl = (SmemCtl *)(smem + kStages * (kAStageBytes + kBStageBytes));
+    float *sstat = (float *)(smem + kStages * (kAStageBytes + kBStageBytes) + 256);     // [2][kMaxStatCh]
+    const bool smem_stats = (p.flags & CONV_F_STATS) && p.tiles_n * p.block_n <= kMaxStatCh;
+    if (smem_stats)
+        for (int i = threadIdx.x; i < 2 * kMaxStatCh; i += kThreads) sstat[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_total = p.tiles_m * p.tiles_n;
@@ -209,7 +214,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             s2[i] = (hi ? s2[i + off] : s2[i]) + r2;
                         }
                     }
-                    if (n0 + lane < p.N) {
+                    if (smem_stats) {            // one global atomic per channel per CTA, at the end
+                        atomicAdd(sstat + n0 + lane, s1[0]);
+                        atomicAdd(sstat + kMaxStatCh + n0 + lane, s2[0]);
+                    } else if (n0 + lane < p.N) {
                         atomicAdd(p.ch_sum + n0 + lane, s1[0]);
                         atomicAdd(p.ch_sqsum + n0 + lane, s2[0]);
                     }
@@ -224,6 +232,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+    if (smem_stats)
+        for (int c = threadIdx.x; c < p.N; c += kThreads) {
+            atomicAdd(p.ch_sum + c, sstat[c]);
+            atomicAdd(p.ch_sqsum + c, sstat[kMaxStatCh + c]);
+        }
 }
 
 // --------------------------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ struct WgradParams {
     int Mpix;                    // total pixels (B*Ho*Wo)
     int Cout, Cin;               // real sizes
     int m_tiles, n_tiles, block_n, ntaps, ksplit, kblocks;   // kblocks = ceil(Mpix/64)
+    int tpc, tap_groups;         // taps handled by one CTA (accumulators tpc * block_n TMEM columns <= 256)
     int b_boxes;                 // block_n / 64 (or 1 when the 64B-swizzle N=32 path is used)
     int b_sw64;                  // 1: X has 32 channels, single [64 px x 32 ch] box, 64B swizzle
     int a_matrix;                // 1: X is a plain matrix (tiled TMA), only with ntaps == 1
@@ -58,7 +59,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     // decode the work item
     int item = blockIdx.x;
     const int ks = item % p.ksplit; item /= p.ksplit;
-    const int tap = item % p.ntaps; item /= p.ntaps;
+    const int tg = item % p.tap_groups; item /= p.tap_groups;
+    const int tap0 = tg * p.tpc, ntap = min(p.tpc, p.ntaps - tap0);
     const int n_blk = item % p.n_tiles;
     const int m_blk = item / p.n_tiles;
     const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
@@ -81,7 +83,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         if (warp == 0) {
             if (lane == 0) {
                 const int a_boxes = (m_blk * 128 + 64 < p.Cout) ? 2 : 1;       // skip a fully out-of-range box
-                const uint32_t bytes = a_boxes * kPixBlk * 128 + (p.b_sw64 ? kPixBlk * 64 : p.b_boxes * kPixBlk * 128);
+                const uint32_t b_tap_bytes = p.b_sw64 ? kPixBlk * 64 : p.b_boxes * kPixBlk * 128;
+                const uint32_t bytes = a_boxes * kPixBlk * 128 + ntap * b_tap_bytes;
                 int stage = 0; uint32_t phase = 0;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int m0 = kb * kPixBlk;
@@ -98,9 +101,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                         const int rem = m0 - img * (p.Po * p.Qo);
                         const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
                         const int bw = qi * p.tstride + p.lower_w, bh = pi * p.tstride + p.lower_h;
-                        for (int bx = 0; bx < p.b_boxes; ++bx)
-                            tma_load_im2col_4d(&tmX, &ctl->full[stage], sB + stage * kWBStage + bx * (kPixBlk * 128),
-                                               n_blk * p.block_n + bx * 64, bw, bh, img, (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
+                        for (int t = 0; t < ntap; ++t)
+                            for (int bx = 0; bx < p.b_boxes; ++bx)
+                                tma_load_im2col_4d(&tmX, &ctl->full[stage], sB + stage * kWBStage + t * b_tap_bytes + bx * (kPixBlk * 128),
+                                                   n_blk * p.block_n + bx * 64, bw, bh, img, (uint16_t)p.tap_ow[tap0 + t],
+                                                   (uint16_t)p.tap_oh[tap0 + t]);
                     }
                     if (++stage == kWStages) { stage = 0; phase ^= 1; }
                 }
@@ -113,14 +118,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(sA + stage * kWAStage);
-                    const uint32_t b_addr = smem_u32(sB + stage * kWBStage);
+                    const uint32_t b_tap_bytes = p.b_sw64 ? kPixBlk * 64 : p.b_boxes * kPixBlk * 128;
+                    for (int t = 0; t < ntap; ++t) {
+                        const uint32_t b_addr = smem_u32(sB + stage * kWBStage) + t * b_tap_bytes;
 #pragma unroll
-                    for (int k = 0; k < kPixBlk / 16; ++k) {
-                        // 16 pixels = two 8-row groups: advance 16 rows of 128 B (64 B in the 64B-swizzle case)
-                        const uint64_t ad = make_smem_desc(a_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
-                        const uint64_t bd = p.b_sw64 ? make_smem_desc(b_addr + k * 16 * 64, 0, 512, SW_64B)
-                                                     : make_smem_desc(b_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
-                        umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                        for (int k = 0; k < kPixBlk / 16; ++k) {
+                            // 16 pixels = two 8-row groups: advance 16 rows of 128 B (64 B in the 64B-swizzle case)
+                            const uint64_t ad = make_smem_desc(a_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
+                            const uint64_t bd = p.b_sw64 ? make_smem_desc(b_addr + k * 16 * 64, 0, 512, SW_64B)
+                                                         : make_smem_desc(b_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
+                            umma_f16(tmem_base + t * p.block_n, ad, bd, idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(&ctl->empty[stage]);
                     if (kb == nkb - 1) umma_commit(&ctl->tmem_full);
@@ -133,16 +141,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             const int co = m_blk * 128 + quarter * 32 + lane;
             mbar_wait(&ctl->tmem_full, 0);
             tc_fence_after();
-            float *row = p.dw + (int64_t)co * p.dw_row + (int64_t)tap * p.cin_pad;
-            for (int c = 0; c < p.block_n / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
-                tmem_ld_wait();
-                const int ci0 = n_blk * p.block_n + c * 32;
-                if (co < p.Cout) {
+            for (int t = 0; t < ntap; ++t) {
+                float *row = p.dw + (int64_t)co * p.dw_row + (int64_t)(tap0 + t) * p.cin_pad;
+                for (int c = 0; c < p.block_n / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.block_n + c * 32, v);
+                    tmem_ld_wait();
+                    const int ci0 = n_blk * p.block_n + c * 32;
+                    if (co < p.Cout) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (ci0 + i < p.Cin) atomicAdd(row + ci0 + i, __uint_as_float(v[i]));
+                        for (int i = 0; i < 32; i += 4)       // Cin is a multiple of 4: 16-byte vector reductions
+                            if (ci0 + i < p.Cin)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci0 + i), "f"(__uint_as_float(v[i])),
+                                             "f"(__uint_as_float(v[i + 1])), "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                                             : "memory");
+                    }
                 }
             }
         }
@@ -165,7 +178,7 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     CY4_CHECK_ARG(d->ldy >= cout64 && d->ldy % 8 == 0, "cy4_conv_wgrad: dy must be allocated with ld >= Cout rounded up to 64");
     const bool sw64 = d->Cin == 32;     // one [64 px x 32 ch] box, 64B swizzle: never reads past the 32 channels
     const int cin64 = sw64 ? 32 : (d->Cin + 63) / 64 * 64;
-    CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx >= cin64 && d->ldx % 8 == 0, "cy4_conv_wgrad: x must be allocated with ld >= Cin rounded up to 64 (or Cin == 32)");
+    CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx >= (sw64 ? 32 : cin64) && d->ldx % 8 == 0, "cy4_conv_wgrad: x must be allocated with ld >= Cin rounded up to 64 (or Cin == 32)");
     WgradParams p;
     memset(&p, 0, sizeof(p));
     p.Mpix = d->B * d->Ho * d->Wo;
@@ -177,8 +190,13 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     p.b_sw64 = sw64 ? 1 : 0;
     p.ntaps = k * k;
     p.kblocks = (p.Mpix + kPixBlk - 1) / kPixBlk;
-    const int items = p.m_tiles * p.n_tiles * p.ntaps;
-    p.ksplit = std::max(1, std::min(p.kblocks, (3 * sm_count() + items - 1) / items));
+    // several taps per CTA while their accumulators (tpc * block_n columns) and X slabs (<= 32 KB per
+    // stage) fit: dY is then loaded once per tap group instead of once per tap
+    p.tpc = std::max(1, std::min(p.ntaps, 256 / p.block_n));
+    if (p.ntaps == 9) p.tpc = p.tpc >= 5 ? 5 : (p.tpc >= 3 ? 3 : p.tpc);      // balanced groups: 5+4, 3+3+3, 2+2+2+2+1
+    p.tap_groups = (p.ntaps + p.tpc - 1) / p.tpc;
+    const int items = p.m_tiles * p.n_tiles * p.tap_groups;
+    p.ksplit = std::max(1, std::min(p.kblocks, (2 * sm_count() + items - 1) / items));
     p.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
     if (p.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_wgrad: matrix mode needs a 1x1/s1/p0 conv");
     p.Po = d->Ho; p.Qo = d->Wo; p.tstride = d->stride; p.lower_w = p.lower_h = -d->pad;

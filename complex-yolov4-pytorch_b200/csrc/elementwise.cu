@@ -83,44 +83,68 @@ __global__ void bn_finalize_kernel(const float *__restrict__ ch_sum, const float
     rstd_out[c] = rstd;
 }
 
+// ---- column-owner mapping for the BN/activation passes -------------------------------------------
+// A thread owns ONE 8-channel vector column (its per-channel parameters stay in registers) and walks
+// down the rows, kUnroll rows per iteration with all loads issued before any math (memory-level
+// parallelism); a block covers (256 / vectors-per-row) rows at a time, so a warp always touches whole
+// 128-byte lines.  vectors-per-row > 256 (C > 2048) is handled by an outer loop.
+constexpr int kUnroll = 4;
+
 // out = act(y * scale + shift) (+ residual)
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__restrict__ scale, const float *__restrict__ shift, int act,
                   const __half *__restrict__ res, int64_t ldr, __half *__restrict__ out, int64_t ldo, int64_t M, int C)
 {
     const int vpr = C >> 3;
-    const int64_t total = M * vpr;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t m = i / vpr;
-        const int c0 = (int)(i - m * vpr) << 3;
-        float f[8], r[8];
-        unpack8(*(const uint4 *)(y + m * ldy + c0), f);
-        const float4 s0 = __ldg((const float4 *)(scale + c0)), s1 = __ldg((const float4 *)(scale + c0 + 4));
-        const float4 h0 = __ldg((const float4 *)(shift + c0)), h1 = __ldg((const float4 *)(shift + c0 + 4));
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    for (int v0 = 0; v0 < vpr; v0 += 256) {
+        const int nv = min(256, vpr - v0);
+        const int rpi = 256 / nv;
+        const int vec = threadIdx.x % nv, rsub = threadIdx.x / nv;
+        if (rsub >= rpi) continue;
+        const int c0 = (v0 + vec) << 3;
+        float sc[8], sh[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = act_f(fmaf(f[k], sc[k], sh[k]), act);
-        if (res) {
-            unpack8(*(const uint4 *)(res + m * ldr + c0), r);
+        for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+        const int64_t step = (int64_t)gridDim.x * rpi;
+        for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += step * kUnroll) {
+            uint4 vy[kUnroll], vr[kUnroll];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] += r[k];
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t mm = m + u * step;
+                if (mm < M) {
+                    vy[u] = *(const uint4 *)(y + mm * ldy + c0);
+                    if (res) vr[u] = *(const uint4 *)(res + mm * ldr + c0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t mm = m + u * step;
+                if (mm < M) {
+                    float f[8], r[8];
+                    unpack8(vy[u], f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] = act_f(fmaf(f[k], sc[k], sh[k]), act);
+                    if (res) {
+                        unpack8(vr[u], r);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] += r[k];
+                    }
+                    *(uint4 *)(out + mm * ldo + c0) = pack8(f);
+                }
+            }
         }
-        *(uint4 *)(out + m * ldo + c0) = pack8(f);
     }
 }
 
-// Per-channel sums of dz = dA * act'(z) and dz * xhat  (xhat = (y - mean) * rstd).
-// Thread = one 8-channel vector column, striding over rows; block partials via shared memory;
-// one atomicAdd per channel per block.
+// Per-channel sums of dz = dA * act'(z) and dz * xhat  (xhat = (y - mean) * rstd), accumulated as
+// sum dz and sum dz*y per thread and combined as rstd * (sum dz*y - mean * sum dz).
 __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
                          const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                          const float *__restrict__ rstd, int act, int64_t M, int C, float *__restrict__ sum_dz,
                          float *__restrict__ sum_dzx)
 {
-    const int vpr = C >> 3;                       // vectors per row
-    const int rows_per_it = 256 / min(vpr, 256);  // rows a block covers per iteration (vpr <= 256 handled below)
+    const int vpr = C >> 3;
     __shared__ float red[2][256][8 + 1];
     for (int v0 = 0; v0 < vpr; v0 += 256) {
         const int nv = min(256, vpr - v0);
@@ -129,41 +153,52 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half
         float a1[8], a2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+        const int c0 = (v0 + vec) << 3;
         if (rsub < rpi) {
-            const int c0 = (v0 + vec) << 3;
-            float sc[8], sh[8], mu[8], rs[8];
+            float sc[8], sh[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; }
-            for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += (int64_t)gridDim.x * rpi) {
-                float fy[8], fg[8];
-                unpack8(*(const uint4 *)(y + m * ldy + c0), fy);
-                unpack8(*(const uint4 *)(dA + m * ldg + c0), fg);
+            for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+            const int64_t step = (int64_t)gridDim.x * rpi;
+            for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += step * kUnroll) {
+                uint4 vy[kUnroll], vg[kUnroll];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float z = fmaf(fy[k], sc[k], sh[k]);
-                    const float dz = fg[k] * act_grad_f(z, act);
-                    a1[k] += dz;
-                    a2[k] += dz * ((fy[k] - mu[k]) * rs[k]);
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int64_t mm = m + u * step;
+                    if (mm < M) { vy[u] = *(const uint4 *)(y + mm * ldy + c0); vg[u] = *(const uint4 *)(dA + mm * ldg + c0); }
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int64_t mm = m + u * step;
+                    if (mm < M) {
+                        float fy[8], fg[8];
+                        unpack8(vy[u], fy); unpack8(vg[u], fg);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float dz = fg[k] * act_grad_f(fmaf(fy[k], sc[k], sh[k]), act);
+                            a1[k] += dz;
+                            a2[k] = fmaf(dz, fy[k], a2[k]);
+                        }
+                    }
                 }
             }
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) { red[0][threadIdx.x][k] = a1[k]; red[1][threadIdx.x][k] = a2[k]; }
         __syncthreads();
-        // threads 0 .. nv*8-1 : channel (t>>3 vector, t&7 lane) sums over the rpi row groups
         for (int t = threadIdx.x; t < nv * 8; t += 256) {
             const int vv = t >> 3, kk = t & 7;
             float s1 = 0.f, s2 = 0.f;
             for (int r = 0; r < rpi; ++r) { s1 += red[0][r * nv + vv][kk]; s2 += red[1][r * nv + vv][kk]; }
-            atomicAdd(sum_dz + ((v0 + vv) << 3) + kk, s1);
-            atomicAdd(sum_dzx + ((v0 + vv) << 3) + kk, s2);
+            const int c = ((v0 + vv) << 3) + kk;
+            atomicAdd(sum_dz + c, s1);
+            atomicAdd(sum_dzx + c, rstd[c] * (s2 - mean[c] * s1));
         }
         __syncthreads();
     }
-    (void)rows_per_it;
 }
 
 // dY = scale * (dz - sum_dz/M - xhat * sum_dzx/M)   (training-mode BN backward; eval: dY = scale*dz)
+//    = scale * dz + A * y + B   with  A = -scale*rstd*sum_dzx/M,  B = -scale*sum_dz/M - A*mean
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
@@ -171,27 +206,45 @@ bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half 
                         float inv_count, int training, int act, __half *__restrict__ dY, int64_t ldd, int64_t M, int C)
 {
     const int vpr = C >> 3;
-    const int64_t total = M * vpr;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t m = i / vpr;
-        const int c0 = (int)(i - m * vpr) << 3;
-        float fy[8], fg[8], o[8];
-        unpack8(*(const uint4 *)(y + m * ldy + c0), fy);
-        unpack8(*(const uint4 *)(dA + m * ldg + c0), fg);
+    for (int v0 = 0; v0 < vpr; v0 += 256) {
+        const int nv = min(256, vpr - v0);
+        const int rpi = 256 / nv;
+        const int vec = threadIdx.x % nv, rsub = threadIdx.x / nv;
+        if (rsub >= rpi) continue;
+        const int c0 = (v0 + vec) << 3;
+        float sc[8], sh[8], A[8], Bc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int c = c0 + k;
-            const float sc = __ldg(scale + c);
-            const float z = fmaf(fy[k], sc, __ldg(shift + c));
-            const float dz = fg[k] * act_grad_f(z, act);
+            sc[k] = scale[c]; sh[k] = shift[c];
             if (training) {
-                const float xh = (fy[k] - __ldg(mean + c)) * __ldg(rstd + c);
-                o[k] = sc * (dz - __ldg(sum_dz + c) * inv_count - xh * __ldg(sum_dzx + c) * inv_count);
-            } else {
-                o[k] = sc * dz;
+                A[k] = -sc[k] * rstd[c] * sum_dzx[c] * inv_count;
+                Bc[k] = -sc[k] * sum_dz[c] * inv_count - A[k] * mean[c];
+            } else { A[k] = 0.f; Bc[k] = 0.f; }
+        }
+        const int64_t step = (int64_t)gridDim.x * rpi;
+        for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += step * kUnroll) {
+            uint4 vy[kUnroll], vg[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t mm = m + u * step;
+                if (mm < M) { vy[u] = *(const uint4 *)(y + mm * ldy + c0); vg[u] = *(const uint4 *)(dA + mm * ldg + c0); }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t mm = m + u * step;
+                if (mm < M) {
+                    float fy[8], fg[8], o[8];
+                    unpack8(vy[u], fy); unpack8(vg[u], fg);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float dz = fg[k] * act_grad_f(fmaf(fy[k], sc[k], sh[k]), act);
+                        o[k] = fmaf(sc[k], dz, fmaf(A[k], fy[k], Bc[k]));
+                    }
+                    *(uint4 *)(dY + mm * ldd + c0) = pack8(o);
+                }
             }
         }
-        *(uint4 *)(dY + m * ldd + c0) = pack8(o);
     }
 }
 
@@ -368,6 +421,16 @@ static inline int ew_grid(int64_t total)
     return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 16));
 }
 
+// grid for the column-owner kernels: enough blocks for ~4 resident 256-thread blocks per SM, but
+// no more than one block per kUnroll row groups
+static inline int col_grid(int64_t M, int C)
+{
+    const int vpr = C / 8;
+    const int rpi = std::max(1, 256 / std::min(vpr, 256));
+    const int64_t groups = (M + (int64_t)rpi * kUnroll - 1) / ((int64_t)rpi * kUnroll);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)sm_count() * 4));
+}
+
 }  // namespace cy4
 
 using namespace cy4;
@@ -394,7 +457,7 @@ int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *
     EW_CHECK_C(C, "cy4_bn_act_fwd");
     CY4_CHECK_ARG(y && scale && shift && out && M >= 0 && (ldy % 8) == 0 && (ldo % 8) == 0 && (ldr % 8) == 0, "cy4_bn_act_fwd: bad argument");
     if (M == 0) return 0;
-    bn_act_fwd_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, act, (const __half *)residual,
+    bn_act_fwd_kernel<<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, act, (const __half *)residual,
                                                                               ldr, (__half *)out, ldo, M, C);
     return cy4_launch_status("cy4_bn_act_fwd");
 }
@@ -405,10 +468,7 @@ int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, const void *dA, int64_t ld
     EW_CHECK_C(C, "cy4_bn_act_bwd_reduce");
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && M >= 0, "cy4_bn_act_bwd_reduce: bad argument");
     if (M == 0) return 0;
-    const int vpr = C / 8;
-    const int rpi = std::max(1, 256 / std::min(vpr, 256));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((M + rpi - 1) / rpi, (int64_t)sm_count() * 8));
-    bn_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift, mean, rstd,
+    bn_act_bwd_reduce_kernel<<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift, mean, rstd,
                                                                      act, M, C, sum_dz, sum_dzx);
     return cy4_launch_status("cy4_bn_act_bwd_reduce");
 }
@@ -420,7 +480,7 @@ int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg
     EW_CHECK_C(C, "cy4_bn_act_bwd_apply");
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && dY && M >= 0, "cy4_bn_act_bwd_apply: bad argument");
     if (M == 0) return 0;
-    bn_act_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift,
+    bn_act_bwd_apply_kernel<<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift,
                                                                                     mean, rstd, sum_dz, sum_dzx, inv_count, training, act,
                                                                                     (__half *)dY, ldd, M, C);
     return cy4_launch_status("cy4_bn_act_bwd_apply");
