@@ -111,9 +111,10 @@ __global__ void pack_dgrad_kernel(const float *__restrict__ w, int Cout, int Cin
     }
 }
 
-__global__ void unpack_wgrad_kernel(const float *__restrict__ acc, int Cout, int Cin, int k, int cin_pad, float scale, int accumulate,
-                                    float *__restrict__ gw)
+__global__ void unpack_wgrad_kernel(const float *__restrict__ acc, int Cout, int Cin, int k, int cin_pad, float scale,
+                                    const float *__restrict__ dscale, int accumulate, float *__restrict__ gw)
 {
+    if (dscale) scale *= __ldg(dscale);
     // gw[co][ci][r][s] (+)= scale * acc[co][r*k+s][ci]
     const int64_t total = (int64_t)Cout * Cin * k * k;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -266,13 +267,13 @@ int cy4_pack_weight_dgrad(const float *w_oihw, int Cout, int Cin, int ksize, voi
     return cy4_launch_status("cy4_pack_weight_dgrad");
 }
 
-int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_pad, float scale, int accumulate, float *gw_oihw,
-                     void *stream)
+int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_pad, float scale, const float *dscale, int accumulate,
+                     float *gw_oihw, void *stream)
 {
     CY4_CHECK_ARG(dw_acc && gw_oihw && Cout > 0 && Cin > 0 && ksize > 0 && cin_pad >= Cin, "cy4_unpack_wgrad: bad argument");
     const int64_t total = (int64_t)Cout * Cin * ksize * ksize;
     const int grid = (int)std::min<int64_t>((total + 255) / 256, 4096);
-    unpack_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dw_acc, Cout, Cin, ksize, cin_pad, scale, accumulate, gw_oihw);
+    unpack_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dw_acc, Cout, Cin, ksize, cin_pad, scale, dscale, accumulate, gw_oihw);
     return cy4_launch_status("cy4_unpack_wgrad");
 }
 

@@ -381,9 +381,10 @@ maxpool_bwd_kernel(const __half *__restrict__ in, int64_t ldi, const __half *__r
 }
 // gin (+)= fp32 scratch
 __global__ void __launch_bounds__(256)
-f32_to_f16_accum_kernel(const float *__restrict__ src, int64_t lds, float scale, __half *__restrict__ dst, int64_t ldd, int64_t M, int C,
-                        int accumulate)
+f32_to_f16_accum_kernel(const float *__restrict__ src, int64_t lds, float scale, const float *__restrict__ dscale,
+                        __half *__restrict__ dst, int64_t ldd, int64_t M, int C, int accumulate)
 {
+    if (dscale) scale *= __ldg(dscale);
     const int vpr = C >> 3;
     const int64_t total = M * vpr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -403,6 +404,30 @@ f32_to_f16_accum_kernel(const float *__restrict__ src, int64_t lds, float scale,
 }
 
 // per-channel column sums of a fp32 [M, ld] matrix (bias gradient of the head convs)
+// max |x| over a fp32 buffer -> atomicMax on the bit pattern (non-negative floats order like ints)
+__global__ void absmax_f32_kernel(const float *__restrict__ src, int64_t n, float *__restrict__ out)
+{
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(src[i]);
+        m = (v > m || v != v) ? v : m;             // NaN propagates
+    }
+    for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, m, o); m = (t > m || t != t) ? t : m; }
+    if ((threadIdx.x & 31) == 0) atomicMax((int *)out, __float_as_int(m != m ? INFINITY : m));
+}
+// scale[0] = 2^k with amax * 2^k ~ target (clamped), scale[1] = 1 / scale[0]; amax == 0 / inf -> 1
+__global__ void make_scale_kernel(const float *__restrict__ amax, float target, float *__restrict__ scale)
+{
+    const float a = amax[0];
+    float s = 1.f;
+    if (a > 0.f && a < INFINITY) {
+        int e = (int)floorf(log2f(target / a));
+        e = max(-14, min(24, e));
+        s = exp2f((float)e);
+    }
+    scale[0] = s; scale[1] = 1.f / s;
+}
+
 __global__ void colsum_f32_kernel(const float *__restrict__ src, int64_t lds, int64_t M, int C, float scale, float *__restrict__ out, int accumulate)
 {
     const int c = blockIdx.x;
@@ -530,13 +555,29 @@ int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, 
     return cy4_launch_status("cy4_maxpool_bwd");
 }
 
-int cy4_f32_to_f16(const float *src, int64_t lds, float scale, void *dst, int64_t ldd, int64_t M, int C, int accumulate, void *stream)
+int cy4_f32_to_f16(const float *src, int64_t lds, float scale, const float *dscale, void *dst, int64_t ldd, int64_t M, int C,
+                   int accumulate, void *stream)
 {
     EW_CHECK_C(C, "cy4_f32_to_f16");
     CY4_CHECK_ARG(src && dst && M >= 0 && (lds % 4) == 0 && (ldd % 8) == 0, "cy4_f32_to_f16: bad argument");
     if (M == 0) return 0;
-    f32_to_f16_accum_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(src, lds, scale, (__half *)dst, ldd, M, C, accumulate);
+    f32_to_f16_accum_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(src, lds, scale, dscale, (__half *)dst, ldd, M, C, accumulate);
     return cy4_launch_status("cy4_f32_to_f16");
+}
+
+int cy4_absmax_f32(const float *src, int64_t n, float *amax, void *stream)
+{
+    CY4_CHECK_ARG(src && amax && n >= 0, "cy4_absmax_f32: bad argument");
+    if (n == 0) return 0;
+    absmax_f32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, n, amax);
+    return cy4_launch_status("cy4_absmax_f32");
+}
+
+int cy4_make_scale(const float *amax, float target, float *scale2, void *stream)
+{
+    CY4_CHECK_ARG(amax && scale2 && target > 0.f, "cy4_make_scale: bad argument");
+    make_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(amax, target, scale2);
+    return cy4_launch_status("cy4_make_scale");
 }
 
 int cy4_colsum_f32(const float *src, int64_t lds, int64_t M, int C, float scale, float *out, int accumulate, void *stream)

@@ -23,7 +23,9 @@ SIGS = {
     "cy4_conv_wgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
     "cy4_pack_weight_fprop": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_vp]),
     "cy4_pack_weight_dgrad": (c_i, [c_f, c_i, c_i, c_i, c_f, c_vp]),
-    "cy4_unpack_wgrad": (c_i, [c_f, c_i, c_i, c_i, c_i, ctypes.c_float, c_i, c_f, c_vp]),
+    "cy4_unpack_wgrad": (c_i, [c_f, c_i, c_i, c_i, c_i, ctypes.c_float, c_f, c_i, c_f, c_vp]),
+    "cy4_absmax_f32": (c_i, [c_f, c_i64, c_f, c_vp]),
+    "cy4_make_scale": (c_i, [c_f, ctypes.c_float, c_f, c_vp]),
     "cy4_bn_finalize": (c_i, [c_f, c_f, ctypes.c_float, c_f, c_f, c_f, c_f, c_f, ctypes.c_float, ctypes.c_float, c_i, c_i,
                                 c_f, c_f, c_f, c_f, c_vp]),
     "cy4_bn_act_fwd": (c_i, [c_f, c_i64, c_f, c_f, c_i, c_f, c_i64, c_f, c_i64, c_i64, c_i, c_vp]),
@@ -35,7 +37,7 @@ SIGS = {
     "cy4_upsample2x_bwd": (c_i, [c_f, c_i64, c_f, c_i64, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "cy4_maxpool_fwd": (c_i, [c_f, c_i64, c_f, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "cy4_maxpool_bwd": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
-    "cy4_f32_to_f16": (c_i, [c_f, c_i64, ctypes.c_float, c_f, c_i64, c_i64, c_i, c_i, c_vp]),
+    "cy4_f32_to_f16": (c_i, [c_f, c_i64, ctypes.c_float, c_f, c_f, c_i64, c_i64, c_i, c_i, c_vp]),
     "cy4_colsum_f32": (c_i, [c_f, c_i64, c_i64, c_i, ctypes.c_float, c_f, c_i, c_vp]),
     "cy4_stem_im2col": (c_i, [c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_vp]),
 }

@@ -101,6 +101,6 @@ def unpack_wgrad(acc, Cout, Cin, k, scale=1.0, out=None, accumulate=False):
     L = _lib.lib()
     if out is None:
         out = torch.empty(Cout, Cin, k, k, device=acc.device, dtype=torch.float32)
-    _lib.check(L.cy4_unpack_wgrad(acc.data_ptr(), Cout, Cin, k, acc.shape[-1], float(scale), 1 if accumulate else 0,
+    _lib.check(L.cy4_unpack_wgrad(acc.data_ptr(), Cout, Cin, k, acc.shape[-1], float(scale), None, 1 if accumulate else 0,
                                   out.data_ptr(), _lib.stream()), "unpack_wgrad")
     return out

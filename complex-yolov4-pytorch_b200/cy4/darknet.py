@@ -172,7 +172,7 @@ class Darknet(nn.Module):
         self.header = torch.IntTensor([0, 0, 0, 0])
         self.seen = 0
         # engine knobs
-        self.grad_scale = 1024.0        # static loss scale of the fp16 gradient tensors (undone in fp32)
+        self.grad_scale_target = 256.0  # the fp16 gradient tensors are scaled so that max |d loss / d head| ~ this
         self.sync_outputs = False       # True: the CPU detections are complete when forward returns (training)
         self._engine = None
 

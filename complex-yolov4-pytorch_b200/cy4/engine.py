@@ -11,7 +11,8 @@ Layout in HBM (per plan = per input shape):
   * fp32 master weights stay in the nn.Parameters; K-major fp16 packs for fprop / dgrad are rebuilt
     when the parameter version changes; weight gradients are accumulated in fp32 ([Cout][tap][Cin])
     and unpacked into one flat OIHW gradient buffer whose slices are returned as the .grad tensors;
-  * gradient tensors are fp16 scaled by `model.grad_scale` (static loss scale, undone in fp32).
+  * gradient tensors are fp16 under a per-step power-of-two loss scale chosen on the device from
+    max |d loss / d head| (target `model.grad_scale_target`), undone in fp32 -- no host sync.
 
 The whole network + loss is ONE autograd node (`_NetFn`): train.py's `loss.backward()` runs the
 backward plan, DDP sees ordinary parameter gradients.
@@ -145,7 +146,7 @@ class Plan:
         self.device = device
         self.B, cin, self.H, self.W = xshape
         assert cin == 3, "the BEV input has 3 channels"
-        self.S = float(model.grad_scale)
+        self.scale_target = float(model.grad_scale_target)
         self.fwd_ops, self.bwd_ops = [], []
         self.params = None
         self._pinned = None
@@ -465,14 +466,27 @@ class Plan:
     def backward(self, gloss):
         L = self.L
         st = _lib.stream()
-        B, S = self.B, self.S
+        B = self.B
         model = self.model
         training = model.training
         dev = self.device
         if self.dy_scratch is None:
             self.dy_scratch = torch.zeros(self._max_dy, device=dev, dtype=torch.float16)
-        g = (gloss.reshape(-1)[:1].to(torch.float32) * S).contiguous()
+            self.gscale = torch.zeros(3, device=dev, dtype=torch.float32)      # [S, 1/S, amax]
+        g = gloss.reshape(-1)[:1].to(torch.float32).contiguous()
         self.dbn.zero_()
+        # head gradients first (fp32, unscaled), then the loss scale of everything below them
+        self.gscale[2:].zero_()
+        for y in self.yolos:
+            head = y["head"]
+            P = head["P"]
+            ldp, G = P.ld, y["G"]
+            self._call(L.cy4_yolo_loss_bwd, ctypes.byref(y["desc"]), P.buf.data_ptr(), y["anchors4"].data_ptr(),
+                       self._tg.data_ptr() if y["nT"] else None, y["nT"], g.data_ptr(), y["ws"].data_ptr(),
+                       head["dP"].data_ptr(), G * G * ldp, 1, G * ldp, ldp, st)
+            self._call(L.cy4_absmax_f32, head["dP"].data_ptr(), head["dP"].numel(), self.gscale[2:].data_ptr(), st)
+            head["has_grad"] = True
+        self._call(L.cy4_make_scale, self.gscale[2:].data_ptr(), self.scale_target, self.gscale.data_ptr(), st)
         # gradient state of every storage
         storages = set()
         for rec in self.convs:
@@ -518,16 +532,7 @@ class Plan:
         for ind in sorted(events, reverse=True):
             kind, r = events[ind]
             if kind == "yolo":
-                y = r
-                head = y["head"]
-                P = head["P"]
-                d = y["desc"]
-                ldp = P.ld
-                G = y["G"]
-                self._call(L.cy4_yolo_loss_bwd, ctypes.byref(d), P.buf.data_ptr(), y["anchors4"].data_ptr(),
-                           self._tg.data_ptr() if y["nT"] else None, y["nT"], g.data_ptr(), y["ws"].data_ptr(),
-                           head["dP"].data_ptr(), G * G * ldp, 1, G * ldp, ldp, st)
-                head["has_grad"] = True
+                pass                                     # done above
             elif kind == "conv":
                 rec = r
                 self._conv_backward(rec, training, st, gw_flat, grads)
@@ -555,7 +560,7 @@ class Plan:
                 self.pool_scratch[:need].zero_()
                 self._call(L.cy4_maxpool_bwd, src.ptr, src.ld, stg.grad.data_ptr(), stg.ld, self.pool_scratch.data_ptr(), B, Hi, Wi, src.C,
                            k, stride, pad, st)
-                self._call(L.cy4_f32_to_f16, self.pool_scratch.data_ptr(), src.C, 1.0, src.gptr, src.ld, B * Hi * Wi, src.C,
+                self._call(L.cy4_f32_to_f16, self.pool_scratch.data_ptr(), src.C, 1.0, None, src.gptr, src.ld, B * Hi * Wi, src.C,
                            1 if src.st.gstate else 0, st)
                 src.st.gstate = 1
             elif kind == "up":
@@ -567,7 +572,7 @@ class Plan:
                 src.st.gstate = 1
 
         # BN parameter gradients: d beta = sum dz, d gamma = sum dz*xhat (both carry the loss scale)
-        gbn = self.dbn * (1.0 / S)
+        gbn = self.dbn * self.gscale[1]
         for rec in self.convs:
             if rec["bn"] is not None and rec.get("bn_bwd_done"):
                 c0, C = rec["coff"], rec["Cout"]
@@ -577,7 +582,8 @@ class Plan:
 
     def _conv_backward(self, rec, training, st, gw_flat, grads):
         L = self.L
-        B, S = self.B, self.S
+        B = self.B
+        inv_s = self.gscale[1:2]
         k, stride, pad, Cout, Cin = rec["k"], rec["stride"], rec["pad"], rec["Cout"], rec["Cin"]
         conv = rec["conv"]
         dy = self.dy_scratch
@@ -604,11 +610,11 @@ class Plan:
             M = P.M
             ldy = 64
             cpad = rup(Cout, 32)
-            # dP (fp32, already carries the loss scale through gloss) -> fp16 dY [M, 64]
-            self._call(L.cy4_f32_to_f16, rec["dP"].data_ptr(), P.ld, 1.0, dy.data_ptr(), ldy, M, cpad, 0, st)
+            # dP (fp32, true gradient) -> fp16 dY [M, 64] under the loss scale
+            self._call(L.cy4_f32_to_f16, rec["dP"].data_ptr(), P.ld, 1.0, self.gscale.data_ptr(), dy.data_ptr(), ldy, M, cpad, 0, st)
             if conv.bias is not None:
                 gb = torch.empty(Cout, device=self.device, dtype=torch.float32)
-                self._call(L.cy4_colsum_f32, rec["dP"].data_ptr(), P.ld, M, Cout, 1.0 / S, gb.data_ptr(), 0, st)
+                self._call(L.cy4_colsum_f32, rec["dP"].data_ptr(), P.ld, M, Cout, 1.0, gb.data_ptr(), 0, st)
                 grads[id(conv.bias)] = gb
         # input gradient
         if not rec["stem"]:
@@ -622,10 +628,10 @@ class Plan:
         if rec["stem"]:
             d = co.conv_desc(B, rec["Ho"], rec["Wo"], 32, Cout, 1, 1, 0, 32, ldy, co.CONV_A_MATRIX)
             self._call(L.cy4_conv_wgrad, ctypes.byref(d), rec["cols"].buf.data_ptr(), dy.data_ptr(), rec["acc"].data_ptr(), st)
-            gw.copy_((rec["acc"][:Cout, 0, :Cin * k * k] * (1.0 / S)).view(Cout, k, k, Cin).permute(0, 3, 1, 2))
+            gw.copy_((rec["acc"][:Cout, 0, :Cin * k * k] * inv_s).view(Cout, k, k, Cin).permute(0, 3, 1, 2))
         else:
             src = rec["src"]
             d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, ldy, 0)
             self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), st)
-            self._call(L.cy4_unpack_wgrad, rec["acc"].data_ptr(), Cout, Cin, k, Cin, 1.0 / S, 0, gw.data_ptr(), st)
+            self._call(L.cy4_unpack_wgrad, rec["acc"].data_ptr(), Cout, Cin, k, Cin, 1.0, inv_s.data_ptr(), 0, gw.data_ptr(), st)
         grads[id(conv.weight)] = gw

@@ -155,8 +155,9 @@ CY4_API int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void *dy
 
 CY4_API int cy4_pack_weight_fprop(const float *w_oihw, int Cout, int Cin, int ksize, int cin_pad, void *w_packed, void *stream);
 CY4_API int cy4_pack_weight_dgrad(const float *w_oihw, int Cout, int Cin, int ksize, void *w_packed, void *stream);
-CY4_API int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_pad, float scale, int accumulate,
-                             float *gw_oihw, void *stream);
+/* gw_oihw (+)= scale * (dscale ? *dscale : 1) * dw_acc, re-laid out to OIHW */
+CY4_API int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_pad, float scale, const float *dscale,
+                             int accumulate, float *gw_oihw, void *stream);
 /* Stem: x NCHW fp32 [B,3,H,W] -> im2col matrix [B*Ho*Wo, 32] fp16 (27 taps*channels (r,s,c order) + 5 zeros) */
 CY4_API int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int ksize, int stride, int pad,
                             void *cols /* [B*Ho*Wo, 32] fp16 */, void *stream);
@@ -193,8 +194,13 @@ CY4_API int cy4_maxpool_fwd(const void *in, int64_t ldi, void *out, int64_t ldo,
 /* gscratch [B,H,W,C] fp32 (caller-zeroed) += routed gradients; follow with cy4_f32_to_f16 */
 CY4_API int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C,
                             int k, int stride, int pad, void *stream);
-/* dst (+)= fp16(scale * src) */
-CY4_API int cy4_f32_to_f16(const float *src, int64_t lds, float scale, void *dst, int64_t ldd, int64_t M, int C, int accumulate, void *stream);
+/* dst (+)= fp16(scale * (dscale ? *dscale : 1) * src); dscale is a device scalar */
+CY4_API int cy4_f32_to_f16(const float *src, int64_t lds, float scale, const float *dscale, void *dst, int64_t ldd, int64_t M, int C,
+                           int accumulate, void *stream);
+/* Dynamic loss scale of the fp16 gradient tensors: amax[0] = max(amax[0], max|src|) (caller zeroes it);
+ * scale2[0] = 2^k such that amax * 2^k ~ target, scale2[1] = 1 / scale2[0]. */
+CY4_API int cy4_absmax_f32(const float *src, int64_t n, float *amax, void *stream);
+CY4_API int cy4_make_scale(const float *amax, float target, float *scale2, void *stream);
 /* out[c] (+)= scale * sum_m src[m, c]  (bias gradient of the head convs) */
 CY4_API int cy4_colsum_f32(const float *src, int64_t lds, int64_t M, int C, float scale, float *out, int accumulate, void *stream);
 

@@ -9,10 +9,16 @@ from cy4.darknet import Darknet
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "tiny_bs2"
 g = np.load(os.path.join(ROOT, "tests", "golden", "darknet_%s.npz" % tag))
+if len(sys.argv) > 2:
+    model_scale = float(sys.argv[2])
+else:
+    model_scale = None
 cfg = str(g["cfg"])
 torch.manual_seed(0)
 model = Darknet(netdefs.cfg_path(cfg), True).cuda()
 model.train()
+if model_scale is not None:
+    model.grad_scale_target = model_scale
 x = synth.make_bev(int(g["batch"])).cuda()
 tg = torch.tensor(g["targets"]).cuda()
 loss, out = model(x, tg)
@@ -49,7 +55,9 @@ for name, p in model.named_parameters():
     rel = np.abs(got - ref).max() / (gn[1] + 1e-12)
     nrel = abs(p.grad.norm().item() - gn[0]) / (gn[0] + 1e-12)
     gw = max(gw, rel)
-    if rel > 0.02 or nrel > 0.02:
+    if not torch.isfinite(p.grad).all():
+        print("NONFINITE grad", name, int((~torch.isfinite(p.grad)).sum()))
+    if rel > 0.05 or nrel > 0.05:
         print("grad %-40s maxerr/maxabs %.3e  norm rel %.3e" % (name, rel, nrel))
 print("worst grad err/max", gw)
 for li, yl in enumerate(model.yolo_layers):
