@@ -1,6 +1,7 @@
 // conv_api.cu -- C-ABI of the convolution stack: fprop / dgrad launch set-up (tensor maps, tap
 // tables, tile shapes), weight packing, stem im2col.  Kernels live in conv_tc.cu / conv_wgrad.cu.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "conv_tc.cuh"
@@ -15,6 +16,8 @@ static int pick_block_n(int cout_pad)
         if (cout_pad % bn == 0) return bn;
     return 32;
 }
+
+static const bool g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;   // debugging aid
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
 struct GenericConv {
@@ -62,7 +65,15 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     if (rc) return rc;
     rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n, swz, 0);
     if (rc) return rc;
-    return launch_conv_tc(tmA, tmB, p, st);
+    alignas(64) CUtensorMap tmC = tmB;
+    if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {
+        // dense fp16 output: epilogue stages 32-row slabs in swizzled smem and TMA-stores them
+        const int cw = p.block_n >= 64 ? 64 : 32;
+        rc = make_tmap_2d(&tmC, g.y, (uint64_t)g.w_rows_pad, (uint64_t)p.M, (uint64_t)g.ldy * 2, cw, 32, cw * 2, 0);
+        if (rc) return rc;
+        p.flags |= CONV_F_TMA_OUT;
+    }
+    return launch_conv_tc(tmA, tmB, tmC, p, st);
 }
 
 static int check_conv_desc(const cy4_conv_desc *d, const char *who)

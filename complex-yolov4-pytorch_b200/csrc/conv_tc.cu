@@ -31,7 +31,9 @@ constexpr int kThreads = 192;
 constexpr int kAStageBytes = kBlockM * 128;        // 16 KB (kchunk 64) ; 8 KB used when kchunk 32
 constexpr int kBStageBytes = 256 * 128;            // 32 KB (block_n 256, kchunk 64)
 constexpr int kMaxStatCh = 1024;                   // per-CTA shared accumulators for the BN statistics
-constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 256 /*barriers*/ + 2 * kMaxStatCh * 4;
+constexpr int kOutStageBytes = 4 * 32 * 128;       // per epilogue warp: 32 rows x 128 B output slab for the TMA store
+constexpr int kCtlOffset = kStages * (kAStageBytes + kBStageBytes) + kOutStageBytes;
+constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + 256 /*barriers*/ + 2 * kMaxStatCh * 4;
 constexpr uint32_t kTmemCols = 512;
 
 struct SmemCtl {
@@ -40,14 +42,16 @@ struct SmemCtl {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvKParams p)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const ConvKParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = smem + kStages * kAStageBytes;
-    SmemCtl *ctl = (SmemCtl *)(smem + kStages * (kAStageBytes + kBStageBytes));
-    float *sstat = (float *)(smem + kStages * (kAStageBytes + kBStageBytes) + 256);     // [2][kMaxStatCh]
+    uint8_t *sOut = smem + kStages * (kAStageBytes + kBStageBytes);
+    SmemCtl *ctl = (SmemCtl *)(smem + kCtlOffset);
+    float *sstat = (float *)(smem + kCtlOffset + 256);     // [2][kMaxStatCh]
     const bool smem_stats = (p.flags & CONV_F_STATS) && p.tiles_n * p.block_n <= kMaxStatCh;
     if (smem_stats)
         for (int i = threadIdx.x; i < 2 * kMaxStatCh; i += kThreads) sstat[i] = 0.f;
@@ -59,6 +63,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        if (p.flags & CONV_F_TMA_OUT) prefetch_tmap(&tmC);
         for (int s = 0; s < kStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
         fence_barrier_init();
@@ -154,7 +159,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                if (p.flags & CONV_F_OUT_F32) {
+                if (p.flags & CONV_F_TMA_OUT) {
+                    // fp16 slab [32 rows][cw columns] of this warp in swizzled smem, then one TMA store
+                    // (coalesced, clipped to M rows by the tensor map).  cw = 64 (128B swizzle) or 32 (64B).
+                    uint8_t *slab = sOut + quarter * (32 * 128);
+                    const int cw = p.block_n >= 64 ? 64 : 32;
+                    const int sub = (c * 32) % cw;                  // column offset of this 32-wide chunk inside the slab
+                    if (sub == 0) {                                  // new slab: the previous store must have read it
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                    }
+                    const int rowbytes = cw * 2;
+                    const int xr = cw == 64 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 o; __half2 *ph = (__half2 *)&o;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(f[i + 2 * j], f[i + 2 * j + 1]);
+                        const int chunk = (sub + i) >> 3;            // 16-byte chunk index inside the row
+                        *(uint4 *)(slab + lane * rowbytes + ((chunk ^ xr) << 4)) = o;
+                    }
+                    if (sub + 32 == cw) {                            // slab complete
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, slab, n_blk * p.block_n + c * 32 - sub, m_blk * kBlockM + quarter * 32);
+                            tma_store_commit();
+                        }
+                    }
+                } else if (p.flags & CONV_F_OUT_F32) {
                     if (row_ok) {
                         float *dst = (float *)p.y + orow * p.ldy + n0;
 #pragma unroll
@@ -229,6 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (warp >= 2 && lane == 0 && (p.flags & CONV_F_TMA_OUT)) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
@@ -314,7 +348,7 @@ int make_tmap_im2col(CUtensorMap *tm, const void *base, int C, int W, int H, int
     return 0;
 }
 
-int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvKParams &p, cudaStream_t st)
+int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const ConvKParams &p, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -323,7 +357,7 @@ int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvKPa
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = std::min(tiles, sm_count());
-    conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, p);
+    conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmC, p);
     return cy4_launch_status("conv_tc_kernel");
 }
 

@@ -10,6 +10,7 @@ enum : uint32_t {
     CONV_F_OUT_F32 = 1u,   // fp32 output (+ optional bias) instead of fp16
     CONV_F_STATS = 2u,     // accumulate per-channel sum / sum^2 of the fp32 accumulators
     CONV_F_ACCUM = 4u,     // y += result (fp16 read-modify-write), used by dgrad into shared grads
+    CONV_F_TMA_OUT = 16u,  // internal: fp16 tile staged in swizzled smem and written with TMA stores
 };
 
 constexpr int kMaxTaps = 16;
@@ -36,6 +37,6 @@ int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t out
 int make_tmap_im2col(CUtensorMap *tm, const void *base, int C, int W, int H, int N, int64_t ld, int lower_w, int lower_h,
                      int upper_w, int upper_h, int chan_per_pixel, int pixels_per_col, int tstride, int swizzle_bytes,
                      int dtype_bf16);
-int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const ConvKParams &p, cudaStream_t st);
+int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const ConvKParams &p, cudaStream_t st);
 
 }  // namespace cy4

@@ -81,6 +81,17 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap *m, uint64_
         : "memory");
 }
 
+// 2-D tiled store smem -> global (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------
 template <uint32_t NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem)   // whole warp

@@ -42,8 +42,7 @@ class Storage:
         self.M = B * H * W
         self.buf = torch.zeros(B, H, W, self.ld, device=device, dtype=dtype)
         self.grad = None
-        self.gstate = 0          # 0: gradient not written yet in this backward pass
-        self.partial = False     # some consumer writes only a channel slice -> memset first
+        self.gwritten = []       # channel intervals of .grad written so far in this backward pass
 
     def ensure_grad(self):
         if self.grad is None:
@@ -68,6 +67,31 @@ class View:
     @property
     def ld(self):
         return self.st.ld
+
+    def grad_has(self):
+        """True if any part of this view's gradient has been written in the current backward pass."""
+        lo, hi = self.off, self.off + self.C
+        return any(a < hi and lo < b for a, b in self.st.gwritten)
+
+    def grad_mode(self):
+        """Call before writing this view's gradient.  Returns 1 if the kernel must accumulate, 0 if it
+        may overwrite; zero-fills the not-yet-written part when the view is only partly covered."""
+        lo, hi = self.off, self.off + self.C
+        st = self.st
+        st.ensure_grad()
+        inter = sorted((max(a, lo), min(b, hi)) for a, b in st.gwritten if a < hi and lo < b)
+        if not inter:
+            st.gwritten.append((lo, hi))
+            return 0
+        pos = lo
+        for a, b in inter:
+            if a > pos:
+                st.grad[..., pos:a].zero_()
+            pos = max(pos, b)
+        if pos < hi:
+            st.grad[..., pos:hi].zero_()
+        st.gwritten.append((lo, hi))
+        return 1
 
 
 class _NetFn(torch.autograd.Function):
@@ -169,22 +193,109 @@ class Plan:
         if rc < 0:
             _lib.check(rc, fn.__name__)
 
-    def _build(self):
-        model, L, dev, B = self.model, self.L, self.device, self.B
-        blocks = model.blocks
-        outs = {}                       # layer index -> View
-        self.convs = []                 # per conv layer records
-        self.yolos = []
-        cur = None                      # current View (None = the network input)
-        cur_hw = (self.H, self.W)
-        totalC = 0
+    def _analyse(self):
+        """Shape / consumer pre-pass over the cfg blocks.  Decides
+          * shortcut fusion: a conv+BN block whose only consumer is the following [shortcut] adds the
+            residual in its BN/activation pass and writes the shortcut's output directly;
+          * concat placement: a tensor consumed by a multi-layer [route] is produced directly inside
+            that route's buffer (at most one concat per tensor; further concats copy)."""
+        blocks = self.model.blocks
+        info = {}                       # ind -> dict(type, C, H, W, origin, srcs)
+        consumers = {}
+        H, W, C = self.H, self.W, 3
         ind = -2
-        # pass 1: create storages / records
+        prev = None
         for block in blocks:
             ind += 1
             t = block["type"]
             if t == "net":
                 continue
+            srcs = []
+            origin = ind
+            if t == "convolutional":
+                k, s = int(block["size"]), int(block["stride"])
+                pad = (k - 1) // 2 if int(block["pad"]) else 0
+                H, W, C = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1, int(block["filters"])
+                srcs = [prev] if prev is not None else []
+            elif t == "route":
+                ls = [int(i) if int(i) > 0 else int(i) + ind for i in block["layers"].split(",")]
+                srcs = ls
+                H, W = info[ls[0]]["H"], info[ls[0]]["W"]
+                if len(ls) == 1:
+                    g = int(block.get("groups", 1))
+                    C = info[ls[0]]["C"] // g
+                    origin = info[ls[0]]["origin"] if g == 1 else None      # a channel slice is not placeable
+                else:
+                    C = sum(info[l]["C"] for l in ls)
+            elif t == "shortcut":
+                f = int(block["from"])
+                srcs = [f if f > 0 else f + ind, ind - 1]
+            elif t == "maxpool":
+                k, s = int(block["size"]), int(block["stride"])
+                pad = k // 2 if (s == 1 and k % 2) else 0
+                H, W = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+                srcs = [prev]
+            elif t == "upsample":
+                H, W = 2 * H, 2 * W
+                srcs = [prev]
+            elif t == "yolo":
+                srcs = [prev]
+            info[ind] = dict(type=t, C=C, H=H, W=W, origin=origin, srcs=srcs, block=block)
+            for sidx in srcs:
+                consumers.setdefault(sidx, []).append(ind)
+            prev = ind
+        fused = {}                      # shortcut ind -> conv ind (ind - 1)
+        for i, inf in info.items():
+            if inf["type"] == "shortcut":
+                c = i - 1
+                if info[c]["type"] == "convolutional" and int(info[c]["block"]["batch_normalize"]) and consumers.get(c) == [i]:
+                    fused[i] = c
+        placement = {}                  # producing layer -> (route ind, channel offset)
+        for i, inf in info.items():
+            if inf["type"] == "route" and len(inf["srcs"]) > 1:
+                off = 0
+                for sidx in inf["srcs"]:
+                    o = info[sidx]["origin"]
+                    if o is not None and info[o]["type"] == "shortcut" and o in fused:
+                        pass                                    # the fused conv writes the shortcut output
+                    ok = o is not None and o not in placement and info[o]["type"] in ("convolutional", "shortcut", "maxpool", "upsample")
+                    if ok and info[o]["type"] == "convolutional" and not int(info[o]["block"]["batch_normalize"]):
+                        ok = False                              # head convs keep their fp32 buffer
+                    if ok and o in fused.values():
+                        ok = False                              # its output is never materialised
+                    if ok:
+                        placement[o] = (i, off)
+                    off += info[sidx]["C"]
+        return info, consumers, fused, placement
+
+    def _build(self):
+        model, L, dev, B = self.model, self.L, self.device, self.B
+        info, consumers, fused, placement = self._analyse()
+        fused_convs = {c: s for s, c in fused.items()}          # conv ind -> shortcut ind
+        outs = {}                       # layer index -> View
+        self.convs, self.yolos = [], []
+        self.routes, self.shorts, self.pools, self.ups = [], [], [], []
+        cat_storage = {}                # route ind -> Storage
+
+        def cat_of(route_ind):
+            if route_ind not in cat_storage:
+                inf = info[route_ind]
+                cat_storage[route_ind] = Storage(B, inf["H"], inf["W"], inf["C"], dev)
+            return cat_storage[route_ind]
+
+        def out_view(i):
+            """Where layer i's output lives: a slice of a concat buffer or its own storage."""
+            inf = info[i]
+            if i in placement:
+                r, off = placement[i]
+                return View(cat_of(r), off, inf["C"])
+            return View(Storage(B, inf["H"], inf["W"], inf["C"], dev))
+
+        cur = None
+        totalC = 0
+        for ind in sorted(info):
+            inf = info[ind]
+            block, t = inf["block"], inf["type"]
             if t == "convolutional":
                 seq = model.models[ind]
                 conv = seq[0]
@@ -192,64 +303,61 @@ class Plan:
                 k, stride = int(block["size"]), int(block["stride"])
                 pad = (k - 1) // 2 if int(block["pad"]) else 0
                 Cout = int(block["filters"])
-                Hi, Wi = cur_hw
-                Ho, Wo = (Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1
-                rec = dict(ind=ind, conv=conv, bn=bn, k=k, stride=stride, pad=pad, Cout=Cout, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo,
-                           act=ACT.get(block["activation"], 0), src=cur, stem=cur is None, Cin=conv.in_channels)
                 if block["activation"] not in ACT:
                     raise NotImplementedError("activation %s" % block["activation"])
+                src = outs[inf["srcs"][0]] if inf["srcs"] else None
+                Hi, Wi = (info[inf["srcs"][0]]["H"], info[inf["srcs"][0]]["W"]) if inf["srcs"] else (self.H, self.W)
+                rec = dict(ind=ind, conv=conv, bn=bn, k=k, stride=stride, pad=pad, Cout=Cout, Hi=Hi, Wi=Wi, Ho=inf["H"], Wo=inf["W"],
+                           act=ACT[block["activation"]], src=src, stem=src is None, Cin=conv.in_channels, res=None)
                 if rec["stem"]:
                     assert conv.in_channels * k * k <= 32, "stem conv must have C*k*k <= 32"
-                    rec["cols"] = Storage(B, Ho, Wo, 32, dev, ld=32)
+                    rec["cols"] = Storage(B, inf["H"], inf["W"], 32, dev, ld=32)
                 if bn is not None:
-                    rec["Y"] = Storage(B, Ho, Wo, Cout, dev)
-                    rec["A"] = Storage(B, Ho, Wo, Cout, dev)
+                    rec["Y"] = Storage(B, inf["H"], inf["W"], Cout, dev)
+                    if ind in fused_convs:                      # conv + BN + act + residual -> shortcut output
+                        sc = fused_convs[ind]
+                        rec["res"] = outs[info[sc]["srcs"][0]]
+                        rec["A"] = out_view(sc)
+                    else:
+                        rec["A"] = out_view(ind)
                     rec["coff"] = totalC
                     totalC += rup(Cout, 8)
-                    cur = View(rec["A"])
+                    cur = rec["A"]
                 else:
-                    rec["P"] = Storage(B, Ho, Wo, rup(Cout, 32), dev, dtype=torch.float32, ld=rup(Cout, 32))
+                    rec["P"] = Storage(B, inf["H"], inf["W"], rup(Cout, 32), dev, dtype=torch.float32, ld=rup(Cout, 32))
                     rec["dP"] = torch.zeros_like(rec["P"].buf)
                     cur = View(rec["P"])
                 self.convs.append(rec)
-                cur_hw = (Ho, Wo)
-                outs[ind] = cur
+                self.fwd_ops.append(("conv", rec))
             elif t == "route":
-                layers = [int(i) if int(i) > 0 else int(i) + ind for i in block["layers"].split(",")]
-                if len(layers) == 1:
-                    src = outs[layers[0]]
+                ls = inf["srcs"]
+                if len(ls) == 1:
+                    src = outs[ls[0]]
                     g = int(block.get("groups", 1))
-                    if g == 1:
-                        cur = src
-                    else:
-                        gid = int(block["group_id"])
-                        cg = src.C // g
-                        cur = View(src.st, src.off + cg * gid, cg)
-                        src.st.partial = True
+                    cur = src if g == 1 else View(src.st, src.off + (src.C // g) * int(block["group_id"]), src.C // g)
                 else:
-                    srcs = [outs[l] for l in layers]
-                    st0 = srcs[0].st
-                    cat = Storage(B, st0.H, st0.W, sum(s.C for s in srcs), dev)
-                    off = 0
-                    for s in srcs:
-                        self.fwd_ops.append((L.cy4_add_copy, (s.ptr, s.ld, None, 0, cat.buf.data_ptr() + off * 2, cat.ld, cat.M, s.C)))
+                    cat = cat_of(ind)
+                    off, copies = 0, []
+                    for sidx in ls:
+                        s = outs[sidx]
+                        if not (s.st is cat and s.off == off):   # not produced in place: copy
+                            self.fwd_ops.append((L.cy4_add_copy, (s.ptr, s.ld, None, 0, cat.buf.data_ptr() + off * 2, cat.ld, cat.M, s.C)))
+                            copies.append((s, off))
                         off += s.C
                     cur = View(cat)
-                    self._route_recs = getattr(self, "_route_recs", [])
-                    self._route_recs.append((ind, cat, srcs))
-                cur_hw = (cur.st.H, cur.st.W)
-                outs[ind] = cur
+                    if copies:
+                        self.routes.append((ind, cat, copies))
             elif t == "shortcut":
-                frm = int(block["from"])
-                frm = frm if frm > 0 else frm + ind
-                a, b = outs[frm], outs[ind - 1]
                 assert block["activation"] == "linear", "shortcut activation %s" % block["activation"]
-                st = Storage(B, a.st.H, a.st.W, a.C, dev)
-                self.fwd_ops.append((L.cy4_add_copy, (a.ptr, a.ld, b.ptr, b.ld, st.buf.data_ptr(), st.ld, st.M, a.C)))
-                cur = View(st)
-                outs[ind] = cur
-                self._short_recs = getattr(self, "_short_recs", [])
-                self._short_recs.append((ind, st, a, b))
+                a = outs[inf["srcs"][0]]
+                if ind in fused:
+                    cur = outs[ind - 1]                          # already the sum (written by the fused conv)
+                    self.shorts.append((ind, cur, a, None))
+                else:
+                    b = outs[ind - 1]
+                    cur = out_view(ind)
+                    self.fwd_ops.append((L.cy4_add_copy, (a.ptr, a.ld, b.ptr, b.ld, cur.ptr, cur.ld, cur.st.M, a.C)))
+                    self.shorts.append((ind, cur, a, b))
             elif t == "maxpool":
                 k, stride = int(block["size"]), int(block["stride"])
                 if stride == 1 and k % 2:
@@ -258,25 +366,18 @@ class Plan:
                     pad = 0
                 else:
                     raise NotImplementedError("MaxPoolDark (size %d stride %d) is outside the complex-yolov4 cfgs" % (k, stride))
-                Hi, Wi = cur_hw
-                Ho, Wo = (Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1
-                st = Storage(B, Ho, Wo, cur.C, dev)
-                self.fwd_ops.append((L.cy4_maxpool_fwd, (cur.ptr, cur.ld, st.buf.data_ptr(), st.ld, B, Hi, Wi, cur.C, k, stride, pad)))
-                self._pool_recs = getattr(self, "_pool_recs", [])
-                self._pool_recs.append((ind, st, cur, k, stride, pad, Hi, Wi))
-                cur = View(st)
-                cur_hw = (Ho, Wo)
-                outs[ind] = cur
+                src = outs[inf["srcs"][0]]
+                Hi, Wi = info[inf["srcs"][0]]["H"], info[inf["srcs"][0]]["W"]
+                cur = out_view(ind)
+                self.fwd_ops.append((L.cy4_maxpool_fwd, (src.ptr, src.ld, cur.ptr, cur.ld, B, Hi, Wi, src.C, k, stride, pad)))
+                self.pools.append((ind, cur, src, k, stride, pad, Hi, Wi))
             elif t == "upsample":
                 assert int(block["stride"]) == 2
-                Hi, Wi = cur_hw
-                st = Storage(B, 2 * Hi, 2 * Wi, cur.C, dev)
-                self.fwd_ops.append((L.cy4_upsample2x_fwd, (cur.ptr, cur.ld, st.buf.data_ptr(), st.ld, B, Hi, Wi, cur.C)))
-                self._up_recs = getattr(self, "_up_recs", [])
-                self._up_recs.append((ind, st, cur, Hi, Wi))
-                cur = View(st)
-                cur_hw = (2 * Hi, 2 * Wi)
-                outs[ind] = cur
+                src = outs[inf["srcs"][0]]
+                Hi, Wi = info[inf["srcs"][0]]["H"], info[inf["srcs"][0]]["W"]
+                cur = out_view(ind)
+                self.fwd_ops.append((L.cy4_upsample2x_fwd, (src.ptr, src.ld, cur.ptr, cur.ld, B, Hi, Wi, src.C)))
+                self.ups.append((ind, cur, src, Hi, Wi))
             elif t == "yolo":
                 layer = model.models[ind]
                 head = self.convs[-1]
@@ -291,44 +392,58 @@ class Plan:
                             loss=torch.zeros(1, device=dev), metrics=torch.zeros(18, device=dev),
                             status=torch.zeros(1, device=dev, dtype=torch.int32), ws=None, nT=-1)
                 self.yolos.append(yrec)
-                outs[ind] = cur
+                self.fwd_ops.append(("yolo", yrec))
             else:
                 raise NotImplementedError("block type %s" % t)
-            # conv forward ops are appended in order here so that fwd_ops stays in layer order
-            if t == "convolutional":
-                self.fwd_ops.append(("conv", self.convs[-1]))
-            if t == "yolo":
-                self.fwd_ops.append(("yolo", self.yolos[-1]))
+            outs[ind] = cur
+            if t == "convolutional" and ind in fused_convs:
+                outs[ind] = cur                                   # (= the shortcut's tensor; nobody else reads it)
 
         # flat per-channel buffers
         tc = max(totalC, 8)
         f32 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
         self.stats = f32(2, tc)            # sum, sum of squares (zeroed every forward)
         self.bnq = f32(4, tc)              # scale, shift, mean, rstd
-        self.dbn = f32(2, tc)              # d beta, d gamma (scaled by S), zeroed every backward
-        # weight packs / gradient accumulators
-        wtot = 0
+        self.dbn = f32(2, tc)              # d beta, d gamma (under the loss scale), zeroed every backward
+        # weight packs / gradient accumulators ([Cout_pad][taps][Cin] fp32, one flat buffer, one memset)
+        wtot, atot = 0, 0
         for rec in self.convs:
             conv = rec["conv"]
             Cout, Cin, k = rec["Cout"], rec["Cin"], rec["k"]
             rec["woff"] = wtot
             wtot += conv.weight.numel()
+            rec["aoff"] = atot
+            rec["ashape"] = (rup(Cout, 32), 1, 32) if rec["stem"] else (rup(Cout, 32), k * k, Cin)
+            atot += rec["ashape"][0] * rec["ashape"][1] * rec["ashape"][2]
             if rec["stem"]:
                 rec["wf"] = torch.zeros(rup(Cout, 32), 32, device=dev, dtype=torch.float16)
-                rec["acc"] = f32(rup(Cout, 32), 1, 32)
             else:
                 rec["wf"] = torch.empty(rup(Cout, 32), k * k * Cin, device=dev, dtype=torch.float16)
                 cpad = rup(Cout, 32)
                 rec["wd"] = torch.empty(rup(Cin, 32), k * k * cpad, device=dev, dtype=torch.float16)
-                rec["acc"] = f32(rup(Cout, 32), k * k, Cin)
                 if cpad != Cout:
                     rec["w32"] = f32(cpad, Cin, k, k)
             rec["wver"] = -1
-        self.gw_flat = f32(max(wtot, 1))
-        self.gbn_flat = None
+        self.acc_flat = f32(max(atot, 1))
+        for rec in self.convs:
+            n = rec["ashape"][0] * rec["ashape"][1] * rec["ashape"][2]
+            rec["acc"] = self.acc_flat[rec["aoff"]:rec["aoff"] + n].view(rec["ashape"])
+        self.gw_numel = max(wtot, 1)
         self.dy_scratch = None
         self.pool_scratch = None
-        self._build_backward()
+        max_dy = 0
+        for rec in self.convs:
+            max_dy = max(max_dy, rec["Y"].M * rec["Y"].ld if rec["bn"] is not None else rec["P"].M * 64)
+        self._max_dy = max_dy
+        self._storages = set()
+        for rec in self.convs:
+            if "A" in rec:
+                self._storages.add(rec["A"].st)
+        for lst in (self.shorts, self.pools, self.ups):
+            for r in lst:
+                self._storages.add(r[1].st)
+        for st in cat_storage.values():
+            self._storages.add(st)
 
     # ---- forward -----------------------------------------------------------------------------
     def _pack_weights(self, st):
@@ -420,6 +535,7 @@ class Plan:
         if rec["bn"] is not None:
             bn = rec["bn"]
             Y, A = rec["Y"], rec["A"]
+            res = rec["res"]
             c0 = rec["coff"]
             d.ldy = Y.ld
             d.flags = amat | (co.CONV_STATS if training else 0)
@@ -429,7 +545,8 @@ class Plan:
             self._call(L.cy4_bn_finalize, s1, s2, float(Y.M), bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                        bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), float(bn.momentum), float(bn.eps),
                        1 if training else 0, Cout, q[0], q[1], q[2], q[3], st)
-            self._call(L.cy4_bn_act_fwd, Y.buf.data_ptr(), Y.ld, q[0], q[1], rec["act"], None, 0, A.buf.data_ptr(), A.ld, Y.M, Cout, st)
+            self._call(L.cy4_bn_act_fwd, Y.buf.data_ptr(), Y.ld, q[0], q[1], rec["act"], res.ptr if res is not None else None,
+                       res.ld if res is not None else 0, A.ptr, A.ld, Y.M, Cout, st)
         else:
             P = rec["P"]
             d.ldy = P.ld
@@ -451,18 +568,6 @@ class Plan:
         return self._pinned
 
     # ---- backward ----------------------------------------------------------------------------
-    def _build_backward(self):
-        """Nothing is precomputed beyond the records: the backward walk is short Python, the cost is
-        in the kernels."""
-        dev = self.device
-        max_dy = 0
-        for rec in self.convs:
-            if rec["bn"] is not None:
-                max_dy = max(max_dy, rec["Y"].M * rec["Y"].ld)
-            else:
-                max_dy = max(max_dy, rec["P"].M * 64)
-        self._max_dy = max_dy
-
     def backward(self, gloss):
         L = self.L
         st = _lib.stream()
@@ -475,6 +580,9 @@ class Plan:
             self.gscale = torch.zeros(3, device=dev, dtype=torch.float32)      # [S, 1/S, amax]
         g = gloss.reshape(-1)[:1].to(torch.float32).contiguous()
         self.dbn.zero_()
+        self.acc_flat.zero_()
+        for s_ in self._storages:
+            s_.gwritten = []
         # head gradients first (fp32, unscaled), then the loss scale of everything below them
         self.gscale[2:].zero_()
         for y in self.yolos:
@@ -487,89 +595,64 @@ class Plan:
             self._call(L.cy4_absmax_f32, head["dP"].data_ptr(), head["dP"].numel(), self.gscale[2:].data_ptr(), st)
             head["has_grad"] = True
         self._call(L.cy4_make_scale, self.gscale[2:].data_ptr(), self.scale_target, self.gscale.data_ptr(), st)
-        # gradient state of every storage
-        storages = set()
-        for rec in self.convs:
-            for key in ("A", "Y"):
-                if key in rec:
-                    storages.add(rec[key])
-        for lst in ("_route_recs", "_short_recs", "_pool_recs", "_up_recs"):
-            for r in getattr(self, lst, []):
-                storages.add(r[1])
-        for s in storages:
-            s.gstate = 0
-            if s.partial:
-                s.ensure_grad().zero_()
-                s.gstate = 1
-        # param gradient buffers (fresh tensors each backward: autograd may keep what we return)
-        gw_flat = torch.empty_like(self.gw_flat)
+        # param gradient buffer (fresh each backward: autograd may keep what we return)
+        gw_flat = torch.empty(self.gw_numel, device=dev, dtype=torch.float32)
         grads = {}
 
-        # events by layer index, processed from the last layer to the first
         events = {}
         for rec in self.convs:
             events[rec["ind"]] = ("conv", rec)
-        for y in self.yolos:
-            events[y["ind"]] = ("yolo", y)
-        for r in getattr(self, "_route_recs", []):
+        for r in self.routes:
             events[r[0]] = ("route", r)
-        for r in getattr(self, "_short_recs", []):
+        for r in self.shorts:
             events[r[0]] = ("short", r)
-        for r in getattr(self, "_pool_recs", []):
+        for r in self.pools:
             events[r[0]] = ("pool", r)
-        for r in getattr(self, "_up_recs", []):
+        for r in self.ups:
             events[r[0]] = ("up", r)
 
         def accumulate_into(view, src_ptr, src_ld, M):
             """view.grad (+)= src"""
-            stg = view.st
-            if stg.gstate:
+            if view.grad_mode():
                 self._call(L.cy4_add_copy, view.gptr, view.ld, src_ptr, src_ld, view.gptr, view.ld, M, view.C, st)
             else:
                 self._call(L.cy4_add_copy, src_ptr, src_ld, None, 0, view.gptr, view.ld, M, view.C, st)
-                stg.gstate = 1
 
         for ind in sorted(events, reverse=True):
             kind, r = events[ind]
-            if kind == "yolo":
-                pass                                     # done above
-            elif kind == "conv":
-                rec = r
-                self._conv_backward(rec, training, st, gw_flat, grads)
+            if kind == "conv":
+                self._conv_backward(r, training, st, gw_flat, grads)
             elif kind == "route":
-                _, cat, srcs = r
-                if not cat.gstate:
-                    continue
-                off = 0
-                for s in srcs:
-                    accumulate_into(s, cat.grad.data_ptr() + off * 2, cat.ld, cat.M)
-                    off += s.C
+                _, cat, copies = r
+                for s_, off in copies:                   # sources that were copied (not produced in place)
+                    cv = View(cat, off, s_.C)
+                    if cv.grad_has():
+                        accumulate_into(s_, cv.gptr, cat.ld, cat.M)
             elif kind == "short":
-                _, stg, a, b = r
-                if not stg.gstate:
+                _, out, a, b = r
+                if not out.grad_has():
                     continue
-                accumulate_into(a, stg.grad.data_ptr(), stg.ld, stg.M)
-                accumulate_into(b, stg.grad.data_ptr(), stg.ld, stg.M)
+                accumulate_into(a, out.gptr, out.ld, out.st.M)
+                if b is not None:                        # unfused: the conv branch receives the same gradient
+                    accumulate_into(b, out.gptr, out.ld, out.st.M)
             elif kind == "pool":
-                _, stg, src, k, stride, pad, Hi, Wi = r
-                if not stg.gstate:
+                _, out, src, k, stride, pad, Hi, Wi = r
+                if not out.grad_has():
                     continue
                 need = B * Hi * Wi * src.C
                 if self.pool_scratch is None or self.pool_scratch.numel() < need:
                     self.pool_scratch = torch.zeros(need, device=dev, dtype=torch.float32)
                 self.pool_scratch[:need].zero_()
-                self._call(L.cy4_maxpool_bwd, src.ptr, src.ld, stg.grad.data_ptr(), stg.ld, self.pool_scratch.data_ptr(), B, Hi, Wi, src.C,
+                self._call(L.cy4_maxpool_bwd, src.ptr, src.ld, out.gptr, out.ld, self.pool_scratch.data_ptr(), B, Hi, Wi, src.C,
                            k, stride, pad, st)
-                self._call(L.cy4_f32_to_f16, self.pool_scratch.data_ptr(), src.C, 1.0, None, src.gptr, src.ld, B * Hi * Wi, src.C,
-                           1 if src.st.gstate else 0, st)
-                src.st.gstate = 1
+                acc = src.grad_mode()
+                self._call(L.cy4_f32_to_f16, self.pool_scratch.data_ptr(), src.C, 1.0, None, src.gptr, src.ld, B * Hi * Wi, src.C, acc, st)
             elif kind == "up":
-                _, stg, src, Hi, Wi = r
-                if not stg.gstate:
+                _, out, src, Hi, Wi = r
+                if not out.grad_has():
                     continue
-                self._call(L.cy4_upsample2x_bwd, stg.grad.data_ptr(), stg.ld, src.gptr, src.ld, B, Hi, Wi, src.C,
-                           1 if src.st.gstate else 0, st)
-                src.st.gstate = 1
+                acc = src.grad_mode()
+                self._call(L.cy4_upsample2x_bwd, out.gptr, out.ld, src.gptr, src.ld, B, Hi, Wi, src.C, acc, st)
 
         # BN parameter gradients: d beta = sum dz, d gamma = sum dz*xhat (both carry the loss scale)
         gbn = self.dbn * self.gscale[1]
@@ -590,14 +673,14 @@ class Plan:
         rec["bn_bwd_done"] = False
         if rec["bn"] is not None:
             A, Y = rec["A"], rec["Y"]
-            if not A.gstate:
+            if not A.grad_has():
                 return                                   # no gradient reaches this layer
             c0 = rec["coff"]
             q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
             sdz, sdzx = self.dbn[0, c0:].data_ptr(), self.dbn[1, c0:].data_ptr()
-            self._call(L.cy4_bn_act_bwd_reduce, Y.buf.data_ptr(), Y.ld, A.grad.data_ptr(), A.ld, q[0], q[1], q[2], q[3], rec["act"],
+            self._call(L.cy4_bn_act_bwd_reduce, Y.buf.data_ptr(), Y.ld, A.gptr, A.ld, q[0], q[1], q[2], q[3], rec["act"],
                        Y.M, Cout, sdz, sdzx, st)
-            self._call(L.cy4_bn_act_bwd_apply, Y.buf.data_ptr(), Y.ld, A.grad.data_ptr(), A.ld, q[0], q[1], q[2], q[3], sdz, sdzx,
+            self._call(L.cy4_bn_act_bwd_apply, Y.buf.data_ptr(), Y.ld, A.gptr, A.ld, q[0], q[1], q[2], q[3], sdz, sdzx,
                        1.0 / Y.M, 1 if training else 0, rec["act"], dy.data_ptr(), Y.ld, Y.M, Cout, st)
             ldy, M = Y.ld, Y.M
             rec["bn_bwd_done"] = True
@@ -619,11 +702,10 @@ class Plan:
         # input gradient
         if not rec["stem"]:
             src = rec["src"]
-            d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, cpad, k, stride, pad, src.ld, ldy, co.CONV_ACCUM if src.st.gstate else 0)
+            acc = src.grad_mode()
+            d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, cpad, k, stride, pad, src.ld, ldy, co.CONV_ACCUM if acc else 0)
             self._call(L.cy4_conv_dgrad, ctypes.byref(d), dy.data_ptr(), rec["wd"].data_ptr(), src.gptr, st)
-            src.st.gstate = 1
-        # weight gradient
-        rec["acc"].zero_()
+        # weight gradient (accumulator zeroed once per backward with the flat buffer)
         gw = gw_flat[rec["woff"]:rec["woff"] + conv.weight.numel()].view_as(conv.weight)
         if rec["stem"]:
             d = co.conv_desc(B, rec["Ho"], rec["Wo"], 32, Cout, 1, 1, 0, 32, ldy, co.CONV_A_MATRIX)

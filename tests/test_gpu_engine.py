@@ -31,8 +31,14 @@ def _cos(a, b):
 def _engine_acts(model):
     acts = {}
     for rec in model._engine.plan.convs:
-        st = rec["A"] if "A" in rec else rec["P"]
-        acts[rec["ind"]] = st.buf[..., :rec["Cout"]].float().permute(0, 3, 1, 2).contiguous()
+        if rec.get("res") is not None:
+            continue                      # fused conv+BN+act+residual: only the shortcut sum is materialised
+        if "A" in rec:
+            v = rec["A"]
+            t = v.st.buf[..., v.off:v.off + v.C]
+        else:
+            t = rec["P"].buf[..., :rec["Cout"]]
+        acts[rec["ind"]] = t.float().permute(0, 3, 1, 2).contiguous()
     return acts
 
 

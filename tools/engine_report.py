@@ -34,8 +34,11 @@ for rec in plan.convs:
     key = "act%d_idx" % i
     if key not in g.files:
         continue
+    if rec.get("res") is not None:
+        continue
     if "A" in rec:
-        t = rec["A"].buf[..., :rec["Cout"]].float().permute(0, 3, 1, 2).reshape(-1)
+        v = rec["A"]
+        t = v.st.buf[..., v.off:v.off + v.C].float().permute(0, 3, 1, 2).reshape(-1)
     else:
         t = rec["P"].buf[..., :rec["Cout"]].float().permute(0, 3, 1, 2).reshape(-1)
     idx = torch.from_numpy(g[key]).cuda()
