@@ -85,14 +85,33 @@ __global__ void bn_finalize_kernel(const float *__restrict__ ch_sum, const float
 
 // ---- column-owner mapping for the BN/activation passes -------------------------------------------
 // A thread owns ONE 8-channel vector column (its per-channel parameters stay in registers) and walks
-// down the rows, kUnroll rows per iteration with all loads issued before any math (memory-level
-// parallelism); a block covers (256 / vectors-per-row) rows at a time, so a warp always touches whole
-// 128-byte lines.  vectors-per-row > 256 (C > 2048) is handled by an outer loop.
+// down a CONTIGUOUS chunk of rows owned by its block, kUnroll row groups per iteration with all loads
+// issued before any math (memory-level parallelism, sequential DRAM pages per block).  A block covers
+// (256 / vectors-per-row) rows per group, so a warp always touches whole 128-byte lines.
+// vectors-per-row > 256 (C > 2048) is handled by an outer loop.  Templated on the activation so the
+// Mish / LeakyReLU math is branch-free.
 constexpr int kUnroll = 4;
 
+template <int ACT> __device__ __forceinline__ float act_t(float z) { return ACT == ACT_MISH ? mish_f(z) : (ACT == ACT_LEAKY ? (z > 0.f ? z : 0.1f * z) : z); }
+template <int ACT> __device__ __forceinline__ float act_grad_t(float z) { return ACT == ACT_MISH ? mish_grad_f(z) : (ACT == ACT_LEAKY ? (z > 0.f ? 1.f : 0.1f) : 1.f); }
+
+struct RowChunk { int64_t begin, end; };
+__device__ __forceinline__ RowChunk block_rows(int64_t M, int rpi)
+{
+    // rows [begin, end) of this block: equal chunks, multiples of rpi * kUnroll
+    const int64_t unit = (int64_t)rpi * kUnroll;
+    const int64_t units = (M + unit - 1) / unit;
+    const int64_t per = (units + gridDim.x - 1) / gridDim.x;
+    RowChunk r;
+    r.begin = min(M, (int64_t)blockIdx.x * per * unit);
+    r.end = min(M, r.begin + per * unit);
+    return r;
+}
+
 // out = act(y * scale + shift) (+ residual)
-__global__ void __launch_bounds__(256)
-bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__restrict__ scale, const float *__restrict__ shift, int act,
+template <int ACT, bool RES>
+__global__ void __launch_bounds__(256, 3)
+bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__restrict__ scale, const float *__restrict__ shift,
                   const __half *__restrict__ res, int64_t ldr, __half *__restrict__ out, int64_t ldo, int64_t M, int C)
 {
     const int vpr = C >> 3;
@@ -105,26 +124,26 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
         float sc[8], sh[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
-        const int64_t step = (int64_t)gridDim.x * rpi;
-        for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += step * kUnroll) {
+        const RowChunk rc = block_rows(M, rpi);
+        for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
             uint4 vy[kUnroll], vr[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int64_t mm = m + u * step;
-                if (mm < M) {
+                const int64_t mm = m + u * rpi;
+                if (mm < rc.end) {
                     vy[u] = *(const uint4 *)(y + mm * ldy + c0);
-                    if (res) vr[u] = *(const uint4 *)(res + mm * ldr + c0);
+                    if (RES) vr[u] = *(const uint4 *)(res + mm * ldr + c0);
                 }
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int64_t mm = m + u * step;
-                if (mm < M) {
+                const int64_t mm = m + u * rpi;
+                if (mm < rc.end) {
                     float f[8], r[8];
                     unpack8(vy[u], f);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) f[k] = act_f(fmaf(f[k], sc[k], sh[k]), act);
-                    if (res) {
+                    for (int k = 0; k < 8; ++k) f[k] = act_t<ACT>(fmaf(f[k], sc[k], sh[k]));
+                    if (RES) {
                         unpack8(vr[u], r);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) f[k] += r[k];
@@ -138,10 +157,11 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
 
 // Per-channel sums of dz = dA * act'(z) and dz * xhat  (xhat = (y - mean) * rstd), accumulated as
 // sum dz and sum dz*y per thread and combined as rstd * (sum dz*y - mean * sum dz).
-__global__ void __launch_bounds__(256)
+template <int ACT>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
                          const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
-                         const float *__restrict__ rstd, int act, int64_t M, int C, float *__restrict__ sum_dz,
+                         const float *__restrict__ rstd, int64_t M, int C, float *__restrict__ sum_dz,
                          float *__restrict__ sum_dzx)
 {
     const int vpr = C >> 3;
@@ -158,23 +178,23 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half
             float sc[8], sh[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
-            const int64_t step = (int64_t)gridDim.x * rpi;
-            for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += step * kUnroll) {
+            const RowChunk rc = block_rows(M, rpi);
+            for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
                 uint4 vy[kUnroll], vg[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    const int64_t mm = m + u * step;
-                    if (mm < M) { vy[u] = *(const uint4 *)(y + mm * ldy + c0); vg[u] = *(const uint4 *)(dA + mm * ldg + c0); }
+                    const int64_t mm = m + u * rpi;
+                    if (mm < rc.end) { vy[u] = *(const uint4 *)(y + mm * ldy + c0); vg[u] = *(const uint4 *)(dA + mm * ldg + c0); }
                 }
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    const int64_t mm = m + u * step;
-                    if (mm < M) {
+                    const int64_t mm = m + u * rpi;
+                    if (mm < rc.end) {
                         float fy[8], fg[8];
                         unpack8(vy[u], fy); unpack8(vg[u], fg);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            const float dz = fg[k] * act_grad_f(fmaf(fy[k], sc[k], sh[k]), act);
+                            const float dz = fg[k] * act_grad_t<ACT>(fmaf(fy[k], sc[k], sh[k]));
                             a1[k] += dz;
                             a2[k] = fmaf(dz, fy[k], a2[k]);
                         }
@@ -199,11 +219,12 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half
 
 // dY = scale * (dz - sum_dz/M - xhat * sum_dzx/M)   (training-mode BN backward; eval: dY = scale*dz)
 //    = scale * dz + A * y + B   with  A = -scale*rstd*sum_dzx/M,  B = -scale*sum_dz/M - A*mean
-__global__ void __launch_bounds__(256)
+template <int ACT>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                         const float *__restrict__ rstd, const float *__restrict__ sum_dz, const float *__restrict__ sum_dzx,
-                        float inv_count, int training, int act, __half *__restrict__ dY, int64_t ldd, int64_t M, int C)
+                        float inv_count, int training, __half *__restrict__ dY, int64_t ldd, int64_t M, int C)
 {
     const int vpr = C >> 3;
     for (int v0 = 0; v0 < vpr; v0 += 256) {
@@ -222,23 +243,23 @@ bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half 
                 Bc[k] = -sc[k] * sum_dz[c] * inv_count - A[k] * mean[c];
             } else { A[k] = 0.f; Bc[k] = 0.f; }
         }
-        const int64_t step = (int64_t)gridDim.x * rpi;
-        for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += step * kUnroll) {
+        const RowChunk rc = block_rows(M, rpi);
+        for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
             uint4 vy[kUnroll], vg[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int64_t mm = m + u * step;
-                if (mm < M) { vy[u] = *(const uint4 *)(y + mm * ldy + c0); vg[u] = *(const uint4 *)(dA + mm * ldg + c0); }
+                const int64_t mm = m + u * rpi;
+                if (mm < rc.end) { vy[u] = *(const uint4 *)(y + mm * ldy + c0); vg[u] = *(const uint4 *)(dA + mm * ldg + c0); }
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int64_t mm = m + u * step;
-                if (mm < M) {
+                const int64_t mm = m + u * rpi;
+                if (mm < rc.end) {
                     float fy[8], fg[8], o[8];
                     unpack8(vy[u], fy); unpack8(vg[u], fg);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float dz = fg[k] * act_grad_f(fmaf(fy[k], sc[k], sh[k]), act);
+                        const float dz = fg[k] * act_grad_t<ACT>(fmaf(fy[k], sc[k], sh[k]));
                         o[k] = fmaf(sc[k], dz, fmaf(A[k], fy[k], Bc[k]));
                     }
                     *(uint4 *)(dY + mm * ldd + c0) = pack8(o);
@@ -453,7 +474,7 @@ static inline int col_grid(int64_t M, int C)
     const int vpr = C / 8;
     const int rpi = std::max(1, 256 / std::min(vpr, 256));
     const int64_t groups = (M + (int64_t)rpi * kUnroll - 1) / ((int64_t)rpi * kUnroll);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)sm_count() * 4));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)sm_count() * 6));
 }
 
 }  // namespace cy4
@@ -482,8 +503,12 @@ int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *
     EW_CHECK_C(C, "cy4_bn_act_fwd");
     CY4_CHECK_ARG(y && scale && shift && out && M >= 0 && (ldy % 8) == 0 && (ldo % 8) == 0 && (ldr % 8) == 0, "cy4_bn_act_fwd: bad argument");
     if (M == 0) return 0;
-    bn_act_fwd_kernel<<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, act, (const __half *)residual,
-                                                                              ldr, (__half *)out, ldo, M, C);
+#define CY4_FWD(ACT, RES)                                                                                                   \
+    bn_act_fwd_kernel<ACT, RES><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift,      \
+                                                                                  (const __half *)residual, ldr, (__half *)out, ldo, M, C)
+    if (residual) { if (act == ACT_MISH) CY4_FWD(ACT_MISH, true); else if (act == ACT_LEAKY) CY4_FWD(ACT_LEAKY, true); else CY4_FWD(ACT_LINEAR, true); }
+    else { if (act == ACT_MISH) CY4_FWD(ACT_MISH, false); else if (act == ACT_LEAKY) CY4_FWD(ACT_LEAKY, false); else CY4_FWD(ACT_LINEAR, false); }
+#undef CY4_FWD
     return cy4_launch_status("cy4_bn_act_fwd");
 }
 
@@ -493,8 +518,11 @@ int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, const void *dA, int64_t ld
     EW_CHECK_C(C, "cy4_bn_act_bwd_reduce");
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && M >= 0, "cy4_bn_act_bwd_reduce: bad argument");
     if (M == 0) return 0;
-    bn_act_bwd_reduce_kernel<<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift, mean, rstd,
-                                                                     act, M, C, sum_dz, sum_dzx);
+#define CY4_RED(ACT)                                                                                                        \
+    bn_act_bwd_reduce_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, \
+                                                                                    shift, mean, rstd, M, C, sum_dz, sum_dzx)
+    if (act == ACT_MISH) CY4_RED(ACT_MISH); else if (act == ACT_LEAKY) CY4_RED(ACT_LEAKY); else CY4_RED(ACT_LINEAR);
+#undef CY4_RED
     return cy4_launch_status("cy4_bn_act_bwd_reduce");
 }
 
@@ -505,9 +533,12 @@ int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg
     EW_CHECK_C(C, "cy4_bn_act_bwd_apply");
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && dY && M >= 0, "cy4_bn_act_bwd_apply: bad argument");
     if (M == 0) return 0;
-    bn_act_bwd_apply_kernel<<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, shift,
-                                                                                    mean, rstd, sum_dz, sum_dzx, inv_count, training, act,
-                                                                                    (__half *)dY, ldd, M, C);
+#define CY4_APP(ACT)                                                                                                        \
+    bn_act_bwd_apply_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, \
+                                                                                   shift, mean, rstd, sum_dz, sum_dzx, inv_count, training, \
+                                                                                   (__half *)dY, ldd, M, C)
+    if (act == ACT_MISH) CY4_APP(ACT_MISH); else if (act == ACT_LEAKY) CY4_APP(ACT_LEAKY); else CY4_APP(ACT_LINEAR);
+#undef CY4_APP
     return cy4_launch_status("cy4_bn_act_bwd_apply");
 }
 
