@@ -18,6 +18,7 @@ static int pick_block_n(int cout_pad)
 }
 
 static const bool g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;   // debugging aid
+static const int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 2;
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
 struct GenericConv {
@@ -63,7 +64,10 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
         rc = make_tmap_im2col(&tmA, g.a, g.Ca, g.Wa, g.Ha, g.B, g.lda, g.lower_w, g.lower_h, g.upper_w, g.upper_h, p.kchunk,
                               128, g.tstride, swz, 0);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n, swz, 0);
+    // clusters of 2 CTAs share each weight slab through TMA multicast (halves the L2 -> SM weight traffic)
+    p.cluster = (p.tiles_m >= 2 && g_cluster >= 2) ? 2 : 1;
+    if (g_cluster >= 4 && p.tiles_m >= 8 && p.block_n >= 64) p.cluster = 4;
+    rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n / p.cluster, swz, 0);
     if (rc) return rc;
     alignas(64) CUtensorMap tmC = tmB;
     if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {

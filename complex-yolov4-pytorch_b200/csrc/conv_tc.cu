@@ -57,20 +57,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = threadIdx.x; i < 2 * kMaxStatCh; i += kThreads) sstat[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_total = p.tiles_m * p.tiles_n;
+    // Work units: (group of `cluster` consecutive m tiles) x n tile.  The CTAs of a cluster take the m
+    // tiles of one group, walk the same k loop and share every weight slab through TMA multicast.
+    const int cs = p.cluster;
+    const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const int unit0 = cs > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int unit_step = cs > 1 ? (int)ncluster_x() : (int)gridDim.x;
+    const int units = ((p.tiles_m + cs - 1) / cs) * p.tiles_n;
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1);
     const int num_kb = p.ntaps * p.cin_chunks;
     const uint32_t a_bytes = kBlockM * p.kchunk * 2, b_bytes = p.block_n * p.kchunk * 2;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
         if (p.flags & CONV_F_TMA_OUT) prefetch_tmap(&tmC);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(&ctl->tmem_base);
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();          // peers' barriers are initialised before any multicast targets them
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
@@ -78,8 +86,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
-                const int n_blk = t % p.tiles_n, m_blk = t / p.tiles_n;
+            const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
+            for (int t = unit0; t < units; t += unit_step) {
+                const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
                 const int m0 = m_blk * kBlockM;
                 // base pixel of the tile in the im2col "base pixel" space
                 const int img = m0 / (p.Po * p.Qo);
@@ -95,8 +104,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
                         else
                             tma_load_2d(&tmA, &ctl->full[stage], sA + stage * kAStageBytes, cc * p.kchunk, m0);
-                        tma_load_2d(&tmB, &ctl->full[stage], sB + stage * kBStageBytes, p.tap_kofs[tap] + cc * p.kchunk,
-                                    n_blk * p.block_n);
+                        if (cs > 1)
+                            tma_load_2d_mc(&tmB, &ctl->full[stage], sB + stage * kBStageBytes + crank * b_rows * p.kchunk * 2,
+                                           p.tap_kofs[tap] + cc * p.kchunk, n_blk * p.block_n + crank * b_rows, cmask);
+                        else
+                            tma_load_2d(&tmB, &ctl->full[stage], sB + stage * kBStageBytes, p.tap_kofs[tap] + cc * p.kchunk,
+                                        n_blk * p.block_n);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -108,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sw = p.kchunk == 64 ? SW_128B : SW_64B;
         const uint32_t sbo = p.kchunk == 64 ? 1024 : 512;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+        for (int t = unit0; t < units; t += unit_step) {
             mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * p.block_n;
@@ -124,7 +137,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, sbo, sw);
                         umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&ctl->empty[stage]);
+                    if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);      // the slot is free once EVERY CTA has consumed it
+                    else umma_commit(&ctl->empty[stage]);
                     if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
                 }
                 __syncwarp();
@@ -136,8 +150,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
-            const int n_blk = t % p.tiles_n, m_blk = t / p.tiles_n;
+        for (int t = unit0; t < units; t += unit_step) {
+            const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
             const int m = m_blk * kBlockM + quarter * 32 + lane;          // this thread's GEMM row
             const bool row_ok = m < p.M;
             // output row address (dense, or a strided parity class of a larger image)
@@ -265,6 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp >= 2 && lane == 0 && (p.flags & CONV_F_TMA_OUT)) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it
     if (warp == 1) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
     if (smem_stats)
         for (int c = threadIdx.x; c < p.N; c += kThreads) {
@@ -355,9 +370,21 @@ int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtenso
         CY4_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set = true;
     }
-    const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = std::min(tiles, sm_count());
-    conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmC, p);
+    const int cs = p.cluster;
+    const int units = ((p.tiles_m + cs - 1) / cs) * p.tiles_n;
+    const int grid = std::min(units, sm_count() / cs) * cs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cs > 1 ? 1 : 0;
+    CY4_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA, tmB, tmC, p));
     return cy4_launch_status("conv_tc_kernel");
 }
 
