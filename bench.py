@@ -270,7 +270,9 @@ def run_reference(args):
     if rank != 0:
         return None
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    base = cpu_step_baseline(args.cfg, budget_s=max(20.0, 6.0 * (args.steps + args.warmup)))
+    if os.environ.get("CY4_BENCH_TEST_TINY"):       # CPU unit test of the harness: tiny net, tiny budget
+        args.cfg = "complex_yolov4_tiny"
+    base = cpu_step_baseline(args.cfg, budget_s=3.0 if os.environ.get("CY4_BENCH_TEST_TINY") else max(20.0, 6.0 * (args.steps + args.warmup)))
     return {"impl": "reference", "metric": "BEV-images/sec training step (bs=32, 608x608)", "value": base["value"], "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(2e3 / base["value"], 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",

@@ -143,6 +143,54 @@ __global__ void unpack_wgrad_kernel(const float *__restrict__ acc, int Cout, int
     }
 }
 
+// ---- batched variants: one launch for every conv layer of the network ------------------------------
+__global__ void pack_batched_kernel(const cy4_pack_item *__restrict__ items)
+{
+    const cy4_pack_item it = items[blockIdx.y];
+    const float *__restrict__ w = it.w_oihw;
+    const int k = it.ksize, Cin = it.Cin, Cout = it.Cout;
+    const int64_t kk = (int64_t)k * k;
+    if (it.w_fprop) {                       // [cout_pad][r][s][Cin]
+        __half *out = (__half *)it.w_fprop;
+        const int64_t total = (int64_t)it.cout_pad * kk * Cin;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int ci = (int)(i % Cin);
+            const int64_t r = i / Cin;
+            const int tap = (int)(r % kk);
+            const int co = (int)(r / kk);
+            out[i] = __float2half_rn(co < Cout ? w[((int64_t)co * Cin + ci) * kk + tap] : 0.f);
+        }
+    }
+    if (it.w_dgrad) {                       // [cin_pad][r][s][cout_pad]
+        __half *out = (__half *)it.w_dgrad;
+        const int cp = it.cout_pad;
+        const int64_t total = (int64_t)it.cin_pad * kk * cp;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int co = (int)(i % cp);
+            const int64_t r = i / cp;
+            const int tap = (int)(r % kk);
+            const int ci = (int)(r / kk);
+            out[i] = __float2half_rn((co < Cout && ci < Cin) ? w[((int64_t)co * Cin + ci) * kk + tap] : 0.f);
+        }
+    }
+}
+
+__global__ void unpack_batched_kernel(const cy4_unpack_item *__restrict__ items, const float *__restrict__ dscale)
+{
+    const cy4_unpack_item it = items[blockIdx.y];
+    const float scale = dscale ? __ldg(dscale) : 1.f;
+    const int k = it.ksize, Cin = it.Cin;
+    const int64_t kk = (int64_t)k * k;
+    const int64_t total = (int64_t)it.Cout * Cin * kk;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % kk);
+        const int64_t r = i / kk;
+        const int ci = (int)(r % Cin);
+        const int co = (int)(r / Cin);
+        it.gw_oihw[i] = scale * it.dw_acc[((int64_t)co * kk + tap) * Cin + ci];
+    }
+}
+
 __global__ void stem_im2col_kernel(const float *__restrict__ x, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
                                    __half *__restrict__ cols)
 {
@@ -290,6 +338,20 @@ int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_
     const int grid = (int)std::min<int64_t>((total + 255) / 256, 4096);
     unpack_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dw_acc, Cout, Cin, ksize, cin_pad, scale, dscale, accumulate, gw_oihw);
     return cy4_launch_status("cy4_unpack_wgrad");
+}
+
+int cy4_pack_weights_batched(const cy4_pack_item *items_dev, int n, void *stream)
+{
+    CY4_CHECK_ARG(items_dev && n > 0, "cy4_pack_weights_batched: bad argument");
+    pack_batched_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(items_dev);
+    return cy4_launch_status("cy4_pack_weights_batched");
+}
+
+int cy4_unpack_wgrad_batched(const cy4_unpack_item *items_dev, int n, const float *dscale, void *stream)
+{
+    CY4_CHECK_ARG(items_dev && n > 0, "cy4_unpack_wgrad_batched: bad argument");
+    unpack_batched_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(items_dev, dscale);
+    return cy4_launch_status("cy4_unpack_wgrad_batched");
 }
 
 int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int ksize, int stride, int pad, void *cols, void *stream)

@@ -378,26 +378,37 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __half *__restrict__ in, int64_t ldi, const __half *__restrict__ gout, int64_t ldo, float *__restrict__ gscratch,
                    int B, int H, int W, int C, int k, int s, int pad, int Ho, int Wo)
 {
-    const int64_t total = (int64_t)B * Ho * Wo * C;
+    // one thread per (output pixel, 8-channel vector): 16-byte window loads, per-channel first-max tracking
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * Ho * Wo * vpr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / C;
-        const int c = (int)(i - r * C);
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
         const int ow = (int)(r % Wo); r /= Wo;
         const int oh = (int)(r % Ho);
         const int b = (int)(r / Ho);
-        float best = -INFINITY; int bh = -1, bw = -1;
+        float best[8]; int bpos[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bpos[q] = -1; }
         for (int dy = 0; dy < k; ++dy) {
             const int h = oh * s - pad + dy;
             if (h < 0 || h >= H) continue;
             for (int dx = 0; dx < k; ++dx) {
                 const int w = ow * s - pad + dx;
                 if (w < 0 || w >= W) continue;
-                const float v = __half2float(in[(((int64_t)b * H + h) * W + w) * ldi + c]);
-                if (v > best || bh < 0) { best = v; bh = h; bw = w; }
+                float t[8];
+                unpack8(*(const uint4 *)(in + (((int64_t)b * H + h) * W + w) * ldi + c0), t);
+                const int pos = h * W + w;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (t[q] > best[q] || bpos[q] < 0) { best[q] = t[q]; bpos[q] = pos; }
             }
         }
-        const float g = __half2float(gout[(((int64_t)b * Ho + oh) * Wo + ow) * ldo + c]);
-        if (bh >= 0) atomicAdd(gscratch + (((int64_t)b * H + bh) * W + bw) * C + c, g);
+        float g[8];
+        unpack8(*(const uint4 *)(gout + (((int64_t)b * Ho + oh) * Wo + ow) * ldo + c0), g);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (bpos[q] >= 0) atomicAdd(gscratch + ((int64_t)b * H * W + bpos[q]) * C + c0 + q, g[q]);
     }
 }
 // gin (+)= fp32 scratch
@@ -579,9 +590,10 @@ int cy4_maxpool_fwd(const void *in, int64_t ldi, void *out, int64_t ldo, int B, 
 int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C, int k,
                     int stride, int pad, void *stream)
 {
+    EW_CHECK_C(C, "cy4_maxpool_bwd");
     CY4_CHECK_ARG(in && gout && gscratch && k > 0 && stride > 0, "cy4_maxpool_bwd: bad argument");
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    maxpool_bwd_kernel<<<ew_grid((int64_t)B * Ho * Wo * C), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (const __half *)gout, ldo, gscratch,
+    maxpool_bwd_kernel<<<ew_grid((int64_t)B * Ho * Wo * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (const __half *)gout, ldo, gscratch,
                                                                                             B, H, W, C, k, stride, pad, Ho, Wo);
     return cy4_launch_status("cy4_maxpool_bwd");
 }

@@ -17,6 +17,17 @@ class ConvDesc(ctypes.Structure):
 
 PD = ctypes.POINTER(ConvDesc)
 
+
+class PackItem(ctypes.Structure):
+    _fields_ = [("w_oihw", ctypes.c_void_p), ("w_fprop", ctypes.c_void_p), ("w_dgrad", ctypes.c_void_p),
+                ("Cout", ctypes.c_int32), ("Cin", ctypes.c_int32), ("ksize", ctypes.c_int32), ("cout_pad", ctypes.c_int32),
+                ("cin_pad", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class UnpackItem(ctypes.Structure):
+    _fields_ = [("dw_acc", ctypes.c_void_p), ("gw_oihw", ctypes.c_void_p), ("Cout", ctypes.c_int32), ("Cin", ctypes.c_int32),
+                ("ksize", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
 SIGS = {
     "cy4_conv_fwd": (c_i, [PD, c_f, c_f, c_f, c_f, c_f, c_f, c_vp]),
     "cy4_conv_dgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
@@ -24,6 +35,8 @@ SIGS = {
     "cy4_pack_weight_fprop": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_vp]),
     "cy4_pack_weight_dgrad": (c_i, [c_f, c_i, c_i, c_i, c_f, c_vp]),
     "cy4_unpack_wgrad": (c_i, [c_f, c_i, c_i, c_i, c_i, ctypes.c_float, c_f, c_i, c_f, c_vp]),
+    "cy4_pack_weights_batched": (c_i, [c_f, c_i, c_vp]),
+    "cy4_unpack_wgrad_batched": (c_i, [c_f, c_i, c_f, c_vp]),
     "cy4_absmax_f32": (c_i, [c_f, c_i64, c_f, c_vp]),
     "cy4_make_scale": (c_i, [c_f, ctypes.c_float, c_f, c_vp]),
     "cy4_bn_finalize": (c_i, [c_f, c_f, ctypes.c_float, c_f, c_f, c_f, c_f, c_f, ctypes.c_float, ctypes.c_float, c_i, c_i,

@@ -419,16 +419,15 @@ class Plan:
                 rec["wf"] = torch.zeros(rup(Cout, 32), 32, device=dev, dtype=torch.float16)
             else:
                 rec["wf"] = torch.empty(rup(Cout, 32), k * k * Cin, device=dev, dtype=torch.float16)
-                cpad = rup(Cout, 32)
-                rec["wd"] = torch.empty(rup(Cin, 32), k * k * cpad, device=dev, dtype=torch.float16)
-                if cpad != Cout:
-                    rec["w32"] = f32(cpad, Cin, k, k)
+                rec["wd"] = torch.empty(rup(Cin, 32), k * k * rup(Cout, 32), device=dev, dtype=torch.float16)
             rec["wver"] = -1
         self.acc_flat = f32(max(atot, 1))
         for rec in self.convs:
             n = rec["ashape"][0] * rec["ashape"][1] * rec["ashape"][2]
             rec["acc"] = self.acc_flat[rec["aoff"]:rec["aoff"] + n].view(rec["ashape"])
         self.gw_numel = max(wtot, 1)
+        self.gw_flat = None
+        self._unpack_dev = None
         self.dy_scratch = None
         self.pool_scratch = None
         max_dy = 0
@@ -447,24 +446,36 @@ class Plan:
 
     # ---- forward -----------------------------------------------------------------------------
     def _pack_weights(self, st):
+        """fp32 OIHW parameters -> K-major fp16 packs, one batched launch, only when a parameter changed."""
+        from ._sigs_engine import PackItem
         L = self.L
+        sig = tuple((rec["conv"].weight._version, rec["conv"].weight.data_ptr()) for rec in self.convs)
+        if sig == getattr(self, "_pack_sig", None):
+            return
+        ptrs = tuple(p for _, p in sig)
+        if ptrs != getattr(self, "_pack_ptrs", None):
+            items = []
+            for rec in self.convs:
+                if rec["stem"]:
+                    continue
+                it = PackItem()
+                w = rec["conv"].weight
+                it.w_oihw, it.w_fprop, it.w_dgrad = w.data_ptr(), rec["wf"].data_ptr(), rec["wd"].data_ptr()
+                it.Cout, it.Cin, it.ksize = rec["Cout"], rec["Cin"], rec["k"]
+                it.cout_pad, it.cin_pad = rup(rec["Cout"], 32), rup(rec["Cin"], 32)
+                items.append(it)
+            arr = (PackItem * len(items))(*items)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+            self._pack_table = host.to(self.device)
+            self._pack_n = len(items)
+            self._pack_ptrs = ptrs
+        self._pack_sig = sig
         for rec in self.convs:
-            w = rec["conv"].weight
-            ver = w._version
-            if rec["wver"] == ver and rec.get("wptr") == w.data_ptr():
-                continue
-            rec["wver"], rec["wptr"] = ver, w.data_ptr()
-            Cout, Cin, k = rec["Cout"], rec["Cin"], rec["k"]
-            if rec["stem"]:
-                # (r, s, c) column order of cy4_stem_im2col, padded to 32
-                rec["wf"][:Cout, :Cin * k * k] = w.detach().permute(0, 2, 3, 1).reshape(Cout, -1).to(torch.float16)
-                continue
-            self._call(L.cy4_pack_weight_fprop, w.data_ptr(), Cout, Cin, k, Cin, rec["wf"].data_ptr(), st)
-            if "w32" in rec:
-                rec["w32"][:Cout] = w.detach()
-                self._call(L.cy4_pack_weight_dgrad, rec["w32"].data_ptr(), rup(Cout, 32), Cin, k, rec["wd"].data_ptr(), st)
-            else:
-                self._call(L.cy4_pack_weight_dgrad, w.data_ptr(), Cout, Cin, k, rec["wd"].data_ptr(), st)
+            if rec["stem"]:       # (r, s, c) column order of cy4_stem_im2col, padded to 32
+                w = rec["conv"].weight
+                rec["wf"][:rec["Cout"], :rec["Cin"] * rec["k"] ** 2] = w.detach().permute(0, 2, 3, 1).reshape(rec["Cout"], -1).to(torch.float16)
+        if self._pack_n:
+            self._call(L.cy4_pack_weights_batched, self._pack_table.data_ptr(), self._pack_n, st)
 
     def forward(self, x, targets, use_giou):
         L = self.L
@@ -596,7 +607,10 @@ class Plan:
             head["has_grad"] = True
         self._call(L.cy4_make_scale, self.gscale[2:].data_ptr(), self.scale_target, self.gscale.data_ptr(), st)
         # param gradient buffer (fresh each backward: autograd may keep what we return)
-        gw_flat = torch.empty(self.gw_numel, device=dev, dtype=torch.float32)
+        if getattr(self, "gw_flat", None) is None:
+            # persistent: autograd clones what we return because we keep a reference (safe with grad accumulation)
+            self.gw_flat = torch.zeros(self.gw_numel, device=dev, dtype=torch.float32)
+        gw_flat = self.gw_flat
         grads = {}
 
         events = {}
@@ -654,6 +668,7 @@ class Plan:
                 acc = src.grad_mode()
                 self._call(L.cy4_upsample2x_bwd, out.gptr, out.ld, src.gptr, src.ld, B, Hi, Wi, src.C, acc, st)
 
+        self._unpack_all(st)
         # BN parameter gradients: d beta = sum dz, d gamma = sum dz*xhat (both carry the loss scale)
         gbn = self.dbn * self.gscale[1]
         for rec in self.convs:
@@ -662,6 +677,28 @@ class Plan:
                 grads[id(rec["bn"].bias)] = gbn[0, c0:c0 + C]
                 grads[id(rec["bn"].weight)] = gbn[1, c0:c0 + C]
         return [grads.get(id(p)) if p.requires_grad else None for p in self.params]
+
+    def _unpack_all(self, st):
+        """[Cout][tap][Cin] fp32 accumulators -> OIHW gradients of every conv, one launch.  The item
+        table is built once per plan: accumulators and the flat gradient buffer are persistent."""
+        from ._sigs_engine import UnpackItem
+        if getattr(self, "_unpack_dev", None) is None:
+            items = []
+            for rec in self.convs:
+                if rec["stem"]:
+                    continue
+                it = UnpackItem()
+                n = rec["conv"].weight.numel()
+                it.dw_acc = rec["acc"].data_ptr()
+                it.gw_oihw = self.gw_flat.data_ptr() + 4 * rec["woff"]
+                it.Cout, it.Cin, it.ksize = rec["Cout"], rec["Cin"], rec["k"]
+                items.append(it)
+            self._unpack_n = len(items)
+            if items:
+                arr = (UnpackItem * len(items))(*items)
+                self._unpack_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(self.device)
+        if self._unpack_n:
+            self._call(self.L.cy4_unpack_wgrad_batched, self._unpack_dev.data_ptr(), self._unpack_n, self.gscale[1:2].data_ptr(), st)
 
     def _conv_backward(self, rec, training, st, gw_flat, grads):
         L = self.L
@@ -715,5 +752,5 @@ class Plan:
             src = rec["src"]
             d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, ldy, 0)
             self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), st)
-            self._call(L.cy4_unpack_wgrad, rec["acc"].data_ptr(), Cout, Cin, k, Cin, 1.0, inv_s.data_ptr(), 0, gw.data_ptr(), st)
+            # (unpacked for all layers by one launch at the end of backward)
         grads[id(conv.weight)] = gw

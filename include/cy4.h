@@ -158,6 +158,20 @@ CY4_API int cy4_pack_weight_dgrad(const float *w_oihw, int Cout, int Cin, int ks
 /* gw_oihw (+)= scale * (dscale ? *dscale : 1) * dw_acc, re-laid out to OIHW */
 CY4_API int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_pad, float scale, const float *dscale,
                              int accumulate, float *gw_oihw, void *stream);
+/* One launch for all conv layers: device arrays of items (pointers are borrowed device pointers). */
+typedef struct cy4_pack_item {
+    const float *w_oihw;     /* [Cout][Cin][k][k] fp32 */
+    void *w_fprop;           /* [cout_pad][k*k][Cin] fp16, or NULL */
+    void *w_dgrad;           /* [cin_pad][k*k][cout_pad] fp16, or NULL */
+    int32_t Cout, Cin, ksize, cout_pad, cin_pad, reserved;
+} cy4_pack_item;
+typedef struct cy4_unpack_item {
+    const float *dw_acc;     /* [Cout_pad][k*k][Cin] fp32 */
+    float *gw_oihw;          /* [Cout][Cin][k][k] fp32 */
+    int32_t Cout, Cin, ksize, reserved;
+} cy4_unpack_item;
+CY4_API int cy4_pack_weights_batched(const cy4_pack_item *items_dev, int n, void *stream);
+CY4_API int cy4_unpack_wgrad_batched(const cy4_unpack_item *items_dev, int n, const float *dscale, void *stream);
 /* Stem: x NCHW fp32 [B,3,H,W] -> im2col matrix [B*Ho*Wo, 32] fp16 (27 taps*channels (r,s,c order) + 5 zeros) */
 CY4_API int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int ksize, int stride, int pad,
                             void *cols /* [B*Ho*Wo, 32] fp16 */, void *stream);
