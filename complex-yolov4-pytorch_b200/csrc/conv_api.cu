@@ -72,7 +72,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     alignas(64) CUtensorMap tmC = tmB;
     if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {
         // dense fp16 output: epilogue stages 32-row slabs in swizzled smem and TMA-stores them
-        const int cw = p.block_n >= 64 ? 64 : 32;
+        const int cw = 32;
         rc = make_tmap_2d(&tmC, g.y, (uint64_t)g.w_rows_pad, (uint64_t)p.M, (uint64_t)g.ldy * 2, cw, 32, cw * 2, 0);
         if (rc) return rc;
         p.flags |= CONV_F_TMA_OUT;

@@ -10,9 +10,10 @@
 //   warp 1      MMA issuer     one lane issues tcgen05.mma (M=128, N=block_n, K=16) on the 128B/64B
 //                              swizzled smem slabs; fp32 accumulators live in TMEM, double buffered
 //                              (2 x block_n columns) so the epilogue of tile i overlaps tile i+1.
-//   warps 2..5  epilogue       tcgen05.ld the accumulator rows, fused per-channel sum / sum^2 for the
-//                              training-mode BatchNorm that follows (warp reduce-scatter + one atomic
-//                              per channel per warp), bias / fp16 or fp32 conversion, store.
+//   warps 2..9  epilogue       two groups of 4 warps, group g drains accumulator stage g (tiles alternate):
+//                              tcgen05.ld the accumulator rows, fused per-channel sum / sum^2 for the
+//                              training-mode BatchNorm that follows (warp reduce-scatter into per-CTA smem
+//                              accumulators), bias / fp16 or fp32 conversion, swizzled smem slab + TMA store.
 // The same kernel serves fprop, stride-1 dgrad (flipped/transposed weights) and the four parity
 // classes of stride-2 dgrad (generic tap table + strided output-row mapping).
 // Reference ops replaced: nn.Conv2d inside src/models/darknet2pytorch.py:247-278 (cuDNN via ATen).
@@ -27,11 +28,11 @@ using namespace sm100;
 
 constexpr int kBlockM = 128;
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                      // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kAStageBytes = kBlockM * 128;        // 16 KB (kchunk 64) ; 8 KB used when kchunk 32
 constexpr int kBStageBytes = 256 * 128;            // 32 KB (block_n 256, kchunk 64)
 constexpr int kMaxStatCh = 1024;                   // per-CTA shared accumulators for the BN statistics
-constexpr int kOutStageBytes = 4 * 32 * 128;       // per epilogue warp: 32 rows x 128 B output slab for the TMA store
+constexpr int kOutStageBytes = 8 * 32 * 64;        // per epilogue warp: 32 rows x 64 B (32 fp16 columns) slab for the TMA store
 constexpr int kCtlOffset = kStages * (kAStageBytes + kBStageBytes) + kOutStageBytes;
 constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + 256 /*barriers*/ + 2 * kMaxStatCh * 4;
 constexpr uint32_t kTmemCols = 512;
@@ -147,10 +148,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int t = unit0; t < units; t += unit_step) {
+        const int group = (warp - 2) >> 2;            // group g owns accumulator stage g
+        const int acc = group; uint32_t acc_phase = 0;
+        int seq = 0;
+        for (int t = unit0; t < units; t += unit_step, ++seq) {
+            if ((seq & 1) != group) continue;
             const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
             const int m = m_blk * kBlockM + quarter * 32 + lane;          // this thread's GEMM row
             const bool row_ok = m < p.M;
@@ -176,15 +180,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.flags & CONV_F_TMA_OUT) {
                     // fp16 slab [32 rows][cw columns] of this warp in swizzled smem, then one TMA store
                     // (coalesced, clipped to M rows by the tensor map).  cw = 64 (128B swizzle) or 32 (64B).
-                    uint8_t *slab = sOut + quarter * (32 * 128);
-                    const int cw = p.block_n >= 64 ? 64 : 32;
-                    const int sub = (c * 32) % cw;                  // column offset of this 32-wide chunk inside the slab
-                    if (sub == 0) {                                  // new slab: the previous store must have read it
-                        if (lane == 0) tma_store_wait_read();
-                        __syncwarp();
-                    }
+                    // (32 columns = 64-byte rows, 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3)
+                    uint8_t *slab = sOut + (warp - 2) * (32 * 64);
+                    const int cw = 32;
+                    const int sub = 0;
+                    if (lane == 0) tma_store_wait_read();            // the previous store must have read the slab
+                    __syncwarp();
                     const int rowbytes = cw * 2;
-                    const int xr = cw == 64 ? (lane & 7) : ((lane >> 1) & 3);
+                    const int xr = (lane >> 1) & 3;
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
                         uint4 o; __half2 *ph = (__half2 *)&o;
@@ -273,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;
         }
     }
     if (warp >= 2 && lane == 0 && (p.flags & CONV_F_TMA_OUT)) tma_store_wait_all();

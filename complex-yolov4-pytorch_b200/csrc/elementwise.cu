@@ -12,23 +12,24 @@ namespace cy4 {
 
 enum { ACT_LINEAR = 0, ACT_LEAKY = 1, ACT_MISH = 2 };
 
-// mish(z) = z * tanh(softplus(z));  tanh(log(1+e^z)) = n / (n + 2),  n = e^z (e^z + 2).
-// softplus threshold 20 as torch (F.softplus): beyond it tanh(.) == 1 in fp32.
+// mish(z) = z * tanh(softplus(z)).  With e = e^z and n = e (e + 2):  tanh(log(1 + e)) = n / (n + 2)
+//   mish  = z - 2 z / (n + 2)
+//   mish' = 1 - 2/(n+2) + 4 z e (e + 1) / (n + 2)^2
+// Both saturate by themselves (e -> inf: 1/(n+2) -> 0 => mish = z, mish' = 1; e -> 0: mish -> 0), which
+// is torch's softplus threshold (20) behaviour to fp32 precision, so no select is needed.  The only
+// hazard is inf * 0 in the derivative, avoided by clamping z at 40 (e^40 squared is still finite).
 __device__ __forceinline__ float mish_f(float z)
 {
-    if (z > 20.f) return z;
-    const float e = __expf(z);
-    const float n = e * (e + 2.f);
-    return z * __fdividef(n, n + 2.f);
+    const float e = __expf(fminf(z, 40.f));
+    const float inv = __fdividef(1.f, fmaf(e, e + 2.f, 2.f));
+    return fmaf(-2.f * z, inv, z);
 }
-// d mish / dz = t + z * t',  t = n/(n+2),  t' = 4 e (e + 1) / (n + 2)^2
 __device__ __forceinline__ float mish_grad_f(float z)
 {
-    if (z > 20.f) return 1.f;
-    const float e = __expf(z);
-    const float n = e * (e + 2.f);
-    const float inv = __fdividef(1.f, n + 2.f);
-    return n * inv + z * 4.f * e * (e + 1.f) * inv * inv;
+    const float e = __expf(fminf(z, 40.f));
+    const float inv = __fdividef(1.f, fmaf(e, e + 2.f, 2.f));
+    const float q = 4.f * z * inv * inv;                  // 4 z / (n+2)^2
+    return fmaf(q, fmaf(e, e, e), fmaf(-2.f, inv, 1.f));
 }
 __device__ __forceinline__ float act_f(float z, int act)
 {
@@ -159,7 +160,7 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
 // sum dz and sum dz*y per thread and combined as rstd * (sum dz*y - mean * sum dz).
 template <int ACT>
 __global__ void __launch_bounds__(256, 2)
-bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
+bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, __half *__restrict__ dA, int64_t ldg,
                          const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
                          const float *__restrict__ rstd, int64_t M, int C, float *__restrict__ sum_dz,
                          float *__restrict__ sum_dzx)
@@ -195,9 +196,11 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float dz = fg[k] * act_grad_t<ACT>(fmaf(fy[k], sc[k], sh[k]));
+                            fg[k] = dz;
                             a1[k] += dz;
                             a2[k] = fmaf(dz, fy[k], a2[k]);
                         }
+                        if (ACT != ACT_LINEAR) *(uint4 *)(dA + mm * ldg + c0) = pack8(fg);   // dz replaces dA (fp16)
                     }
                 }
             }
@@ -219,7 +222,8 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, const __half
 
 // dY = scale * (dz - sum_dz/M - xhat * sum_dzx/M)   (training-mode BN backward; eval: dY = scale*dz)
 //    = scale * dz + A * y + B   with  A = -scale*rstd*sum_dzx/M,  B = -scale*sum_dz/M - A*mean
-template <int ACT>
+// DZ_READY: the reduce pass already replaced dA by dz, so this pass is three FMAs per element.
+template <int ACT, bool DZ_READY>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half *__restrict__ dA, int64_t ldg,
                         const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ mean,
@@ -259,7 +263,7 @@ bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half 
                     unpack8(vy[u], fy); unpack8(vg[u], fg);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float dz = fg[k] * act_grad_t<ACT>(fmaf(fy[k], sc[k], sh[k]));
+                        const float dz = DZ_READY ? fg[k] : fg[k] * act_grad_t<ACT>(fmaf(fy[k], sc[k], sh[k]));
                         o[k] = fmaf(sc[k], dz, fmaf(A[k], fy[k], Bc[k]));
                     }
                     *(uint4 *)(dY + mm * ldd + c0) = pack8(o);
@@ -523,14 +527,14 @@ int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *
     return cy4_launch_status("cy4_bn_act_fwd");
 }
 
-int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
+int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, const float *scale, const float *shift,
                           const float *mean, const float *rstd, int act, int64_t M, int C, float *sum_dz, float *sum_dzx, void *stream)
 {
     EW_CHECK_C(C, "cy4_bn_act_bwd_reduce");
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && M >= 0, "cy4_bn_act_bwd_reduce: bad argument");
     if (M == 0) return 0;
 #define CY4_RED(ACT)                                                                                                        \
-    bn_act_bwd_reduce_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, \
+    bn_act_bwd_reduce_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (__half *)dA, ldg, scale, \
                                                                                     shift, mean, rstd, M, C, sum_dz, sum_dzx)
     if (act == ACT_MISH) CY4_RED(ACT_MISH); else if (act == ACT_LEAKY) CY4_RED(ACT_LEAKY); else CY4_RED(ACT_LINEAR);
 #undef CY4_RED
@@ -539,16 +543,19 @@ int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, const void *dA, int64_t ld
 
 int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
                          const float *mean, const float *rstd, const float *sum_dz, const float *sum_dzx, float inv_count,
-                         int training, int act, void *dY, int64_t ldd, int64_t M, int C, void *stream)
+                         int training, int act, int dz_ready, void *dY, int64_t ldd, int64_t M, int C, void *stream)
 {
     EW_CHECK_C(C, "cy4_bn_act_bwd_apply");
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && dY && M >= 0, "cy4_bn_act_bwd_apply: bad argument");
     if (M == 0) return 0;
-#define CY4_APP(ACT)                                                                                                        \
-    bn_act_bwd_apply_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, scale, \
-                                                                                   shift, mean, rstd, sum_dz, sum_dzx, inv_count, training, \
-                                                                                   (__half *)dY, ldd, M, C)
-    if (act == ACT_MISH) CY4_APP(ACT_MISH); else if (act == ACT_LEAKY) CY4_APP(ACT_LEAKY); else CY4_APP(ACT_LINEAR);
+#define CY4_APP(ACT, RDY)                                                                                                   \
+    bn_act_bwd_apply_kernel<ACT, RDY><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, \
+                                                                                        scale, shift, mean, rstd, sum_dz, sum_dzx, inv_count, \
+                                                                                        training, (__half *)dY, ldd, M, C)
+    // dz_ready: cy4_bn_act_bwd_reduce ran on the same dA buffer before (it leaves dz = dA*act'(z) there)
+    if (dz_ready || act == ACT_LINEAR) CY4_APP(ACT_LINEAR, true);
+    else if (act == ACT_MISH) CY4_APP(ACT_MISH, false);
+    else CY4_APP(ACT_LEAKY, false);
 #undef CY4_APP
     return cy4_launch_status("cy4_bn_act_bwd_apply");
 }

@@ -2,8 +2,8 @@
 interpreter + autograd backward) as a static plan of hand-written sm_100a kernels.
 
 Layout in HBM (per plan = per input shape):
-  * every activation is NHWC fp16 in its own [B*H*W, ld] buffer, ld = channels rounded up to 64
-    (so that the weight-gradient TMA boxes never leave the allocation);
+  * every activation is NHWC fp16 in a [B*H*W, ld] buffer, ld = channels rounded up to 32 (tensors
+    consumed by a multi-input route are produced directly inside the route's buffer);
   * each conv keeps its raw output Y (pre-BatchNorm) and the activated output A; backward
     recomputes BN/activation derivatives from Y instead of storing them;
   * per-channel BN quantities (batch sums, scale/shift, mean/rstd, d gamma, d beta) of ALL layers
@@ -38,7 +38,7 @@ class Storage:
 
     def __init__(self, B, H, W, C, device, dtype=torch.float16, ld=None):
         self.B, self.H, self.W, self.C = B, H, W, C
-        self.ld = ld or rup(C, 64)
+        self.ld = ld or rup(C, 32)
         self.M = B * H * W
         self.buf = torch.zeros(B, H, W, self.ld, device=device, dtype=dtype)
         self.grad = None
@@ -432,7 +432,7 @@ class Plan:
         self.pool_scratch = None
         max_dy = 0
         for rec in self.convs:
-            max_dy = max(max_dy, rec["Y"].M * rec["Y"].ld if rec["bn"] is not None else rec["P"].M * 64)
+            max_dy = max(max_dy, rec["Y"].M * rup(rec["Cout"], 64) if rec["bn"] is not None else rec["P"].M * 64)
         self._max_dy = max_dy
         self._storages = set()
         for rec in self.convs:
@@ -717,9 +717,9 @@ class Plan:
             sdz, sdzx = self.dbn[0, c0:].data_ptr(), self.dbn[1, c0:].data_ptr()
             self._call(L.cy4_bn_act_bwd_reduce, Y.buf.data_ptr(), Y.ld, A.gptr, A.ld, q[0], q[1], q[2], q[3], rec["act"],
                        Y.M, Cout, sdz, sdzx, st)
+            ldy, M = rup(Cout, 64), Y.M                    # the dY scratch keeps 64-channel rows (weight-gradient TMA boxes)
             self._call(L.cy4_bn_act_bwd_apply, Y.buf.data_ptr(), Y.ld, A.gptr, A.ld, q[0], q[1], q[2], q[3], sdz, sdzx,
-                       1.0 / Y.M, 1 if training else 0, rec["act"], dy.data_ptr(), Y.ld, Y.M, Cout, st)
-            ldy, M = Y.ld, Y.M
+                       1.0 / Y.M, 1 if training else 0, rec["act"], 1, dy.data_ptr(), ldy, Y.M, Cout, st)
             rec["bn_bwd_done"] = True
             cpad = Cout
         else:

@@ -192,14 +192,16 @@ CY4_API int cy4_bn_finalize(const float *ch_sum, const float *ch_sqsum, float co
 /* out = act(y*scale + shift) (+ residual) */
 CY4_API int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *shift, int act, const void *residual,
                            int64_t ldr, void *out, int64_t ldo, int64_t M, int C, void *stream);
-/* sum_dz[c] += sum_m dA*act'(z), sum_dzx[c] += sum_m dA*act'(z)*xhat  (= d beta, d gamma) */
-CY4_API int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
+/* sum_dz[c] += sum_m dz, sum_dzx[c] += sum_m dz*xhat (= d beta, d gamma), dz = dA*act'(z).  For a
+ * non-linear activation dA is OVERWRITTEN with dz (fp16) so that the apply pass need not recompute act'. */
+CY4_API int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, const float *scale, const float *shift,
                                   const float *mean, const float *rstd, int act, int64_t M, int C, float *sum_dz, float *sum_dzx,
                                   void *stream);
-/* dY = scale*(dz - sum_dz/M - xhat*sum_dzx/M) (training) or scale*dz (eval) */
+/* dY = scale*(dz - sum_dz/M - xhat*sum_dzx/M) (training) or scale*dz (eval).  dz_ready != 0: dA already
+ * holds dz (cy4_bn_act_bwd_reduce ran on it); otherwise dz = dA*act'(z) is recomputed here. */
 CY4_API int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,
                                  const float *mean, const float *rstd, const float *sum_dz, const float *sum_dzx, float inv_count,
-                                 int training, int act, void *dY, int64_t ldd, int64_t M, int C, void *stream);
+                                 int training, int act, int dz_ready, void *dY, int64_t ldd, int64_t M, int C, void *stream);
 /* out = a (+ b): route copies into / out of concat buffers, shortcut add, gradient accumulation */
 CY4_API int cy4_add_copy(const void *a, int64_t lda, const void *b, int64_t ldb, void *out, int64_t ldo, int64_t M, int C, void *stream);
 CY4_API int cy4_upsample2x_fwd(const void *in, int64_t ldi, void *out, int64_t ldo, int B, int H, int W, int C, void *stream);

@@ -240,6 +240,7 @@ def test_elementwise_kernels_vs_torch():
     for act_id, act in ((2, lambda z: z * torch.tanh(F.softplus(z))), (1, lambda z: F.leaky_relu(z, 0.1)), (0, lambda z: z)):
         y16 = (torch.randn(B, H, W, C, device="cuda") * 1.5 + 0.3).half()
         gA16 = torch.randn(B, H, W, C, device="cuda").half()
+        gA_keep = gA16.clone()            # the reduce pass overwrites dA with dz
         gamma = torch.rand(C, device="cuda") + 0.5; beta = torch.randn(C, device="cuda")
         yf = y16.float().requires_grad_(True)
         s1 = yf.detach().sum((0, 1, 2)).contiguous(); s2 = (yf.detach() ** 2).sum((0, 1, 2)).contiguous()
@@ -255,13 +256,13 @@ def test_elementwise_kernels_vs_torch():
         ref = act(z).permute(0, 2, 3, 1)
         assert (out.float() - ref).abs().max().item() < 4e-3 * ref.abs().max().item() + 2e-3
         assert torch.allclose(rm, rm2, atol=1e-5) and torch.allclose(rv, rv2, rtol=1e-4, atol=1e-5) and int(nbt) == 1
-        ref.backward(gA16.float())
+        ref.backward(gA_keep.float())
         sums = torch.zeros(2, C, device="cuda")
         _lib.check(L.cy4_bn_act_bwd_reduce(y16.data_ptr(), C, gA16.data_ptr(), C, q[0].data_ptr(), q[1].data_ptr(), q[2].data_ptr(),
                                            q[3].data_ptr(), act_id, M, C, sums[0].data_ptr(), sums[1].data_ptr(), st))
         dy = torch.empty_like(y16)
         _lib.check(L.cy4_bn_act_bwd_apply(y16.data_ptr(), C, gA16.data_ptr(), C, q[0].data_ptr(), q[1].data_ptr(), q[2].data_ptr(),
-                                          q[3].data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), 1.0 / M, 1, act_id, dy.data_ptr(), C, M, C, st))
+                                          q[3].data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), 1.0 / M, 1, act_id, 1, dy.data_ptr(), C, M, C, st))
         gref = yf.grad
         assert (dy.float() - gref).abs().max().item() < 5e-3 * gref.abs().max().item() + 1e-3
     # max pool (SPP sizes + 2x2/2) and its gradient routing, upsample
