@@ -12,6 +12,7 @@
 // pixel range); split-K slices add their fp32 partial tile into dw_acc with red.global.add.
 // Reference op replaced: the autograd backward of nn.Conv2d (weight), src/train.py:212.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -32,6 +33,7 @@ struct WgradParams {
     int Cout, Cin;               // real sizes
     int m_tiles, n_tiles, block_n, ntaps, ksplit, kblocks;   // kblocks = ceil(Mpix/64)
     int tpc, tap_groups;         // taps handled by one CTA (accumulators tpc * block_n TMEM columns <= 256)
+    int cluster;                 // CTAs per cluster (consecutive m tiles) sharing every X slab through TMA multicast
     int b_boxes;                 // block_n / 64 (or 1 when the 64B-swizzle N=32 path is used)
     int b_sw64;                  // 1: X has 32 channels, single [64 px x 32 ch] box, 64B swizzle
     int a_matrix;                // 1: X is a plain matrix (tiled TMA), only with ntaps == 1
@@ -56,26 +58,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     WCtl *ctl = (WCtl *)(smem + kWStages * (kWAStage + kWBStage));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // decode the work item
-    int item = blockIdx.x;
+    // decode the work item; the CTAs of a cluster differ only in the m tile
+    const int cs = p.cluster;
+    const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1);
+    int item = blockIdx.x / cs;
     const int ks = item % p.ksplit; item /= p.ksplit;
     const int tg = item % p.tap_groups; item /= p.tap_groups;
     const int tap0 = tg * p.tpc, ntap = min(p.tpc, p.ntaps - tap0);
     const int n_blk = item % p.n_tiles;
-    const int m_blk = item / p.n_tiles;
+    const int m_blk = (item / p.n_tiles) * cs + crank;
     const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
     const int kb0 = ks * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
     const int nkb = kb1 - kb0;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmDy); prefetch_tmap(&tmX);
-        for (int s = 0; s < kWStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
         mbar_init(&ctl->tmem_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(&ctl->tmem_base);
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
@@ -102,10 +108,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                         const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
                         const int bw = qi * p.tstride + p.lower_w, bh = pi * p.tstride + p.lower_h;
                         for (int t = 0; t < ntap; ++t)
-                            for (int bx = 0; bx < p.b_boxes; ++bx)
-                                tma_load_im2col_4d(&tmX, &ctl->full[stage], sB + stage * kWBStage + t * b_tap_bytes + bx * (kPixBlk * 128),
-                                                   n_blk * p.block_n + bx * 64, bw, bh, img, (uint16_t)p.tap_ow[tap0 + t],
-                                                   (uint16_t)p.tap_oh[tap0 + t]);
+                            for (int bx = 0; bx < p.b_boxes; ++bx) {
+                                uint8_t *dst = sB + stage * kWBStage + t * b_tap_bytes + bx * (kPixBlk * 128);
+                                if (cs == 1)
+                                    tma_load_im2col_4d(&tmX, &ctl->full[stage], dst, n_blk * p.block_n + bx * 64, bw, bh, img,
+                                                       (uint16_t)p.tap_ow[tap0 + t], (uint16_t)p.tap_oh[tap0 + t]);
+                                else if ((t * p.b_boxes + bx) % cs == crank)     // this CTA's share, multicast to the cluster
+                                    tma_load_im2col_4d_mc(&tmX, &ctl->full[stage], dst, n_blk * p.block_n + bx * 64, bw, bh, img,
+                                                          (uint16_t)p.tap_ow[tap0 + t], (uint16_t)p.tap_oh[tap0 + t], cmask);
+                            }
                     }
                     if (++stage == kWStages) { stage = 0; phase ^= 1; }
                 }
@@ -130,7 +141,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                             umma_f16(tmem_base + t * p.block_n, ad, bd, idesc, (kb | k) != 0);
                         }
                     }
-                    umma_commit(&ctl->empty[stage]);
+                    if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);
+                    else umma_commit(&ctl->empty[stage]);
                     if (kb == nkb - 1) umma_commit(&ctl->tmem_full);
                 }
                 __syncwarp();
@@ -162,6 +174,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();
     if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
 }
 
@@ -195,6 +208,9 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     p.tpc = std::max(1, std::min(p.ntaps, 256 / p.block_n));
     if (p.ntaps == 9) p.tpc = p.tpc >= 5 ? 5 : (p.tpc >= 3 ? 3 : p.tpc);      // balanced groups: 5+4, 3+3+3, 2+2+2+2+1
     p.tap_groups = (p.ntaps + p.tpc - 1) / p.tpc;
+    // pairs of CTAs on consecutive m tiles share (multicast) the X slabs; not for the matrix (stem) mode
+    static const int g_wcluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 2;
+    p.cluster = (g_wcluster >= 2 && !(d->flags & CY4_CONV_A_MATRIX) && p.m_tiles % 2 == 0) ? 2 : 1;
     const int items = p.m_tiles * p.n_tiles * p.tap_groups;
     p.ksplit = std::max(1, std::min(p.kblocks, (2 * sm_count() + items - 1) / items));
     p.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
@@ -221,6 +237,17 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
         attr_set = true;
     }
     const int grid = items * p.ksplit;
-    conv_wgrad_kernel<<<grid, kWThreads, kWSmem, (cudaStream_t)stream>>>(tmDy, tmX, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kWThreads);
+    cfg.dynamicSmemBytes = kWSmem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.cluster > 1 ? 1 : 0;
+    CY4_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tmDy, tmX, p));
     return cy4_launch_status("cy4_conv_wgrad");
 }

@@ -91,6 +91,17 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *m, uint64_t *b
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_im2col_4d_mc(const CUtensorMap *m, uint64_t *bar, void *dst, int c, int w, int h, int n,
+                                                      uint16_t off_w, uint16_t off_h, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"(off_w), "h"(off_h), "h"(cta_mask)
+        : "memory");
+}
+
 // ---- thread-block clusters ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
