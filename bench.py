@@ -100,6 +100,7 @@ def run_ours(args):
     B = args.batch
     torch.manual_seed(0)
     net = Darknet(netdefs.cfg_path(args.cfg), use_giou_loss=True).to(dev).train()
+    net.use_cuda_graph = bool(args.cuda_graph)
     model = net
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=128)
@@ -172,6 +173,7 @@ def run_ours(args):
         value = world * B * args.steps / (ms_total / 1e3)
         # ---- roofline pass: CUDA-event timing of every tensor-core conv launch for 2 steps
         plan = net._engine.plan
+        net.use_cuda_graph = False          # events around individual launches need eager launches
         plan.prof = []
         for _ in range(2):
             step(x, tg)
@@ -290,6 +292,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--cfg", default="complex_yolov4")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--cuda-graph", dest="cuda_graph", type=int, default=0, help="replay the fwd/bwd launch sequences as CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     res = run_reference(args) if args.impl == "reference" else run_ours(args)

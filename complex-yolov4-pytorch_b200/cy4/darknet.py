@@ -174,6 +174,7 @@ class Darknet(nn.Module):
         # engine knobs
         self.grad_scale_target = 256.0  # the fp16 gradient tensors are scaled so that max |d loss / d head| ~ this
         self.sync_outputs = False       # True: the CPU detections are complete when forward returns (training)
+        self.use_cuda_graph = False     # True: after 2 eager steps the fwd / bwd launch sequences are replayed as CUDA graphs
         self._engine = None
 
     # ------------------------------------------------------------------ forward

@@ -154,11 +154,51 @@ class StepEngine:
                 out_cpu.copy_(out, non_blocking=True)
             return loss, out_cpu
 
+    # ---- optional CUDA-graph replay of the two launch sequences (model.use_cuda_graph) --------------
+    # The plan is static per (input shape, number of targets): after two eager steps the forward and
+    # the backward launch sequences (~430 + ~760 kernels) are captured once and replayed, which removes
+    # the per-launch CPU cost and the inter-kernel gaps.  Inputs / upstream gradient are copied into
+    # static buffers; outputs (loss, metrics, detections, gradients) live in static buffers as well.
     def _forward(self, x, targets):
-        return self.plan.forward(x, targets, self.model.use_giou_loss)
+        plan, model = self.plan, self.model
+        use_graph = bool(getattr(model, "use_cuda_graph", False)) and targets is not None and model.training
+        if not use_graph:
+            plan.graph_state = None
+            return plan.forward(x, targets, model.use_giou_loss)
+        gs = plan.graph_state
+        key = (int(targets.shape[0]), bool(model.use_giou_loss))
+        if gs is None or gs["key"] != key:
+            gs = plan.graph_state = dict(key=key, eager=0, fwd=None, bwd=None, x=torch.empty_like(x, dtype=torch.float32),
+                                         tg=torch.empty(targets.shape, device=x.device, dtype=torch.float32),
+                                         g=torch.ones(1, device=x.device, dtype=torch.float32))
+        if gs["fwd"] is None and gs["eager"] < 2:
+            gs["eager"] += 1
+            return plan.forward(x, targets, model.use_giou_loss)
+        gs["x"].copy_(x)
+        gs["tg"].copy_(targets)
+        if gs["fwd"] is None:
+            plan.force_pack = True
+            gs["fwd"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gs["fwd"]):
+                gs["loss"] = plan.forward(gs["x"], gs["tg"], model.use_giou_loss)
+            plan.force_pack = False
+        gs["fwd"].replay()
+        for y in plan.yolos:
+            y["layer"].metrics = LazyMetrics(y["metrics_out"])
+        return gs["loss"].clone()
 
     def _backward(self, gloss):
-        return self.plan.backward(gloss)
+        plan = self.plan
+        gs = plan.graph_state
+        if gs is None or gs["fwd"] is None:
+            return plan.backward(gloss)
+        gs["g"].copy_(gloss.reshape(-1)[:1])
+        if gs["bwd"] is None:
+            gs["bwd"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gs["bwd"]):
+                gs["grads"] = plan.backward(gs["g"])
+        gs["bwd"].replay()
+        return gs["grads"]
 
 
 class Plan:
@@ -175,6 +215,8 @@ class Plan:
         self.params = None
         self._pinned = None
         self.prof = None             # list -> CUDA-event timing of every conv launch (bench.py roofline pass)
+        self.graph_state = None
+        self.force_pack = False
         self._build()
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -450,7 +492,7 @@ class Plan:
         from ._sigs_engine import PackItem
         L = self.L
         sig = tuple((rec["conv"].weight._version, rec["conv"].weight.data_ptr()) for rec in self.convs)
-        if sig == getattr(self, "_pack_sig", None):
+        if sig == getattr(self, "_pack_sig", None) and not self.force_pack:
             return
         ptrs = tuple(p for _, p in sig)
         if ptrs != getattr(self, "_pack_ptrs", None):
@@ -516,7 +558,8 @@ class Plan:
                     self._call(L.cy4_yolo_loss_fwd, ctypes.byref(d), head["P"].buf.data_ptr(), y["anchors4"].data_ptr(),
                                tg.data_ptr() if nT else None, nT, y["out"].data_ptr(), y["loss"].data_ptr(),
                                y["metrics"].data_ptr(), y["status"].data_ptr(), y["ws"].data_ptr(), st)
-                    layer.metrics = LazyMetrics(y["metrics"].clone())
+                    y["metrics_out"] = y["metrics"].clone()
+                    layer.metrics = LazyMetrics(y["metrics_out"])
                     layer._status = y["status"]
                     if layer.check_targets:
                         check_status(y["status"], "YoloLayer")
