@@ -17,8 +17,11 @@ static int pick_block_n(int cout_pad)
     return 32;
 }
 
-static const bool g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;   // debugging aid
-static const int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 2;
+// Tunables (cy4_set_option).  Weight-slab multicast across 2/4-CTA clusters is implemented and
+// parity-tested, but measured neutral on B200 for these layer shapes, so it is off by default.
+int g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;
+int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 1;
+int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
 struct GenericConv {
@@ -223,6 +226,16 @@ __global__ void stem_im2col_kernel(const float *__restrict__ x, int B, int C, in
 using namespace cy4;
 
 extern "C" {
+
+int cy4_set_option(const char *name, int value)
+{
+    CY4_CHECK_ARG(name, "cy4_set_option: null name");
+    if (!strcmp(name, "conv_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2 || value == 4, "conv_cluster must be 1, 2 or 4"); g_cluster = value; return 0; }
+    if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
+    if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
+    set_error("cy4_set_option: unknown option %s", name);
+    return -1;
+}
 
 int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias, float *ch_sum,
                  float *ch_sqsum, void *stream)

@@ -20,6 +20,7 @@
 
 namespace cy4 {
 using namespace sm100;
+extern int g_wgrad_cluster;      // conv_api.cu (cy4_set_option)
 
 constexpr int kWStages = 4;
 constexpr int kWThreads = 192;
@@ -209,8 +210,7 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     if (p.ntaps == 9) p.tpc = p.tpc >= 5 ? 5 : (p.tpc >= 3 ? 3 : p.tpc);      // balanced groups: 5+4, 3+3+3, 2+2+2+2+1
     p.tap_groups = (p.ntaps + p.tpc - 1) / p.tpc;
     // pairs of CTAs on consecutive m tiles share (multicast) the X slabs; not for the matrix (stem) mode
-    static const int g_wcluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 2;
-    p.cluster = (g_wcluster >= 2 && !(d->flags & CY4_CONV_A_MATRIX) && p.m_tiles % 2 == 0) ? 2 : 1;
+    p.cluster = (g_wgrad_cluster >= 2 && !(d->flags & CY4_CONV_A_MATRIX) && p.m_tiles % 2 == 0) ? 2 : 1;
     const int items = p.m_tiles * p.n_tiles * p.tap_groups;
     p.ksplit = std::max(1, std::min(p.kblocks, (2 * sm_count() + items - 1) / items));
     p.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;

@@ -29,6 +29,7 @@ class UnpackItem(ctypes.Structure):
                 ("ksize", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 SIGS = {
+    "cy4_set_option": (c_i, [ctypes.c_char_p, c_i]),
     "cy4_conv_fwd": (c_i, [PD, c_f, c_f, c_f, c_f, c_f, c_f, c_vp]),
     "cy4_conv_dgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
     "cy4_conv_wgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),

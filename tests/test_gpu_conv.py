@@ -199,3 +199,26 @@ def test_conv_fp32_output_parity():
         y = co.conv_fwd(x, co.pack_fprop(w.float()), Cout, k, stride, pad, out_f32=True)
         ref = _ref_conv(x, w, stride, pad)
         assert (y.cpu() - ref).abs().max().item() <= 1e-3          # measured ~1e-5
+
+
+@pytest.mark.parametrize("option,value", [("conv_cluster", 2), ("conv_cluster", 4), ("wgrad_cluster", 2), ("tma_store", 0)])
+def test_conv_variants(option, value):
+    """The optional code paths (TMA multicast of the weight / activation slabs across thread-block
+    clusters, direct-store epilogue) give the same results as the default configuration."""
+    from cy4 import _lib, convops as co
+    L = _lib.lib()
+    torch.manual_seed(21)
+    B, H, W, Cin, Cout = 2, 38, 38, 256, 512
+    x = torch.randn(B, H, W, Cin, device="cuda").half()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / 48).half()
+    dy = (torch.randn(B, H, W, Cout, device="cuda") / 50).half()
+    wp, wd = co.pack_fprop(w.float()), co.pack_dgrad(w.float())
+    base = (co.conv_fwd(x, wp, Cout, 3, 1, 1), co.conv_dgrad(dy, wd, H, W, Cin, 3, 1, 1), co.conv_wgrad(x, dy, Cin, Cout, 3, 1, 1))
+    default = {"conv_cluster": 1, "wgrad_cluster": 1, "tma_store": 1}[option]
+    try:
+        _lib.check(L.cy4_set_option(option.encode(), value))
+        alt = (co.conv_fwd(x, wp, Cout, 3, 1, 1), co.conv_dgrad(dy, wd, H, W, Cin, 3, 1, 1), co.conv_wgrad(x, dy, Cin, Cout, 3, 1, 1))
+    finally:
+        _lib.check(L.cy4_set_option(option.encode(), default))
+    assert torch.equal(base[0], alt[0]) and torch.equal(base[1], alt[1])
+    assert (base[2] - alt[2]).abs().max().item() <= 1e-3 * base[2].abs().max().item()     # split-K atomics: order only

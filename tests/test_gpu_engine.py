@@ -137,7 +137,7 @@ def test_step_vs_fp16_storage_oracle(golden, tag, cfgname):
     if tag.startswith("tiny"):
         assert abs(loss.item() - ref_loss) <= 2e-3 * ref_loss
         assert worst_act <= 0.05                    # measured 0.032: single fp16-ulp rounding flips, amplified
-        assert worst_cos >= 0.975 and worst_norm <= 0.06
+        assert worst_cos >= 0.975 and worst_norm <= 0.08
     else:
         # 110 randomly initialised convs: a flipped fp16 rounding (one ulp on ~0.1% of the elements)
         # is amplified layer by layer exactly like the rounding itself, so the heads decorrelate even
