@@ -231,6 +231,8 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
         rc = make_tmap_im2col(&tmX, x, cin64, d->Wi, d->Hi, d->B, d->ldx, -d->pad, -d->pad, d->pad - (k - 1), d->pad - (k - 1),
                               sw64 ? 32 : 64, kPixBlk, d->stride, sw64 ? 64 : 128, 0);
     if (rc) return rc;
+    if (d->flags & CY4_CONV_ZERO_ACC)     // zero right before use: the red.global.add then hit lines that are hot in L2
+        CY4_CUDA(cudaMemsetAsync(dw_acc, 0, (size_t)((d->Cout + 31) / 32 * 32) * k * k * d->Cin * sizeof(float), (cudaStream_t)stream));
     static bool attr_set = false;
     if (!attr_set) {
         CY4_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));

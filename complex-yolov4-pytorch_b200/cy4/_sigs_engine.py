@@ -60,3 +60,4 @@ CONV_OUT_F32 = 1
 CONV_STATS = 2
 CONV_ACCUM = 4
 CONV_A_MATRIX = 8
+CONV_ZERO_ACC = 16

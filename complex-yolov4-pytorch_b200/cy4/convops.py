@@ -4,7 +4,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._sigs_engine import CONV_A_MATRIX, CONV_ACCUM, CONV_OUT_F32, CONV_STATS, ConvDesc
+from ._sigs_engine import CONV_A_MATRIX, CONV_ACCUM, CONV_OUT_F32, CONV_STATS, CONV_ZERO_ACC, ConvDesc
 
 
 def rup(x, m):

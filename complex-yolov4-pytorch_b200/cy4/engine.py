@@ -634,7 +634,6 @@ class Plan:
             self.gscale = torch.zeros(3, device=dev, dtype=torch.float32)      # [S, 1/S, amax]
         g = gloss.reshape(-1)[:1].to(torch.float32).contiguous()
         self.dbn.zero_()
-        self.acc_flat.zero_()
         for s_ in self._storages:
             s_.gwritten = []
         # head gradients first (fp32, unscaled), then the loss scale of everything below them
@@ -788,12 +787,12 @@ class Plan:
         # weight gradient (accumulator zeroed once per backward with the flat buffer)
         gw = gw_flat[rec["woff"]:rec["woff"] + conv.weight.numel()].view_as(conv.weight)
         if rec["stem"]:
-            d = co.conv_desc(B, rec["Ho"], rec["Wo"], 32, Cout, 1, 1, 0, 32, ldy, co.CONV_A_MATRIX)
+            d = co.conv_desc(B, rec["Ho"], rec["Wo"], 32, Cout, 1, 1, 0, 32, ldy, co.CONV_A_MATRIX | co.CONV_ZERO_ACC)
             self._call(L.cy4_conv_wgrad, ctypes.byref(d), rec["cols"].buf.data_ptr(), dy.data_ptr(), rec["acc"].data_ptr(), st)
             gw.copy_((rec["acc"][:Cout, 0, :Cin * k * k] * inv_s).view(Cout, k, k, Cin).permute(0, 3, 1, 2))
         else:
             src = rec["src"]
-            d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, ldy, 0)
+            d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, ldy, co.CONV_ZERO_ACC)
             self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), st)
             # (unpacked for all layers by one launch at the end of backward)
         grads[id(conv.weight)] = gw

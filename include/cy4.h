@@ -140,6 +140,7 @@ typedef struct cy4_conv_desc {
                                  statistics of the BatchNorm2d that follows (darknet2pytorch.py:260) */
 #define CY4_CONV_A_MATRIX 8u  /* x is a plain [B*Ho*Wo, Cin] matrix (1x1/s1/p0 only): tiled TMA instead of
                                  im2col TMA -- used for the stem's explicit im2col matrix */
+#define CY4_CONV_ZERO_ACC 16u /* cy4_conv_wgrad: memset dw_acc before accumulating into it */
 #define CY4_CONV_ACCUM   4u   /* y += result instead of y = result (fp16), for gradients of tensors
                                  with several consumers (route / shortcut, darknet2pytorch.py:180-219) */
 

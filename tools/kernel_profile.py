@@ -35,9 +35,12 @@ for e in prof.events():
         name = re.sub(r"<.*", "", e.name.split("(")[0]).replace("void ", "").replace("cy4::", "")[-56:]
         agg[name][0] += 1; agg[name][1] += e.device_time / 1e3 if hasattr(e, "device_time") else e.cuda_time / 1e3
         tot += e.device_time / 1e3 if hasattr(e, "device_time") else e.cuda_time / 1e3
+seq = [(re.sub(r"<.*", "", e.name.split("(")[0]).replace("void ", "").replace("cy4::", ""), (e.device_time if hasattr(e, "device_time") else e.cuda_time))
+       for e in sorted(prof.events(), key=lambda e: e.time_range.start) if e.device_type is not None and "cuda" in str(e.device_type).lower()]
 print("total kernel ms %.2f" % tot)
 rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
 for k, v in rows[:28]:
     print("%-58s n=%4d %8.3f ms %5.1f%%" % (k, v[0], v[1], 100 * v[1] / tot))
 if len(sys.argv) > 3:
-    json.dump({k: v for k, v in rows}, open(sys.argv[3], "w"), indent=1)
+    json.dump({"agg": {k: v for k, v in rows}, "conv_tc_us": [t for n, t in seq if n.endswith("conv_tc_kernel")],
+               "wgrad_us": [t for n, t in seq if n.endswith("conv_wgrad_kernel")]}, open(sys.argv[3], "w"), indent=0)
