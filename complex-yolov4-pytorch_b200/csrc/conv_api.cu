@@ -21,6 +21,8 @@ static int pick_block_n(int cout_pad)
 // parity-tested, but measured neutral on B200 for these layer shapes, so it is off by default.
 int g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;
 int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 1;
+int g_debug = 0;
+int g_resident_b = 1;
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
@@ -51,6 +53,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     p.tiles_n = g.w_rows_pad / p.block_n;
     p.ntaps = g.ntaps;
     p.a_mode = g.a_matrix ? 0 : 1;
+    p.debug = g_debug;
     p.ab_fmt = 0;
     p.Po = g.Po; p.Qo = g.Qo; p.tstride = g.tstride; p.lower_w = g.lower_w; p.lower_h = g.lower_h;
     for (int t = 0; t < g.ntaps; ++t) { p.tap_ow[t] = g.ow[t]; p.tap_oh[t] = g.oh[t]; p.tap_kofs[t] = g.kofs[t]; }
@@ -70,6 +73,12 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     // clusters of 2 CTAs share each weight slab through TMA multicast (halves the L2 -> SM weight traffic)
     p.cluster = (p.tiles_m >= 2 && g_cluster >= 2) ? 2 : 1;
     if (g_cluster >= 4 && p.tiles_m >= 8 && p.block_n >= 64) p.cluster = 4;
+    // whole weight panel resident in smem when it fits the B stage region (128 KB) and there is one n tile
+    p.resident_b = 0;
+    if (g_resident_b && p.tiles_n == 1 && (int64_t)p.block_n * g.w_ktot * 2 <= 4 * 32768 && g.w_ktot % p.kchunk == 0 && p.tiles_m > sm_count()) {
+        p.resident_b = (int)(g.w_ktot / p.kchunk);
+        p.cluster = 1;
+    }
     rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n / p.cluster, swz, 0);
     if (rc) return rc;
     alignas(64) CUtensorMap tmC = tmB;
@@ -233,6 +242,8 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "conv_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2 || value == 4, "conv_cluster must be 1, 2 or 4"); g_cluster = value; return 0; }
     if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
     if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
+    if (!strcmp(name, "resident_weights")) { g_resident_b = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage
     set_error("cy4_set_option: unknown option %s", name);
     return -1;
 }

@@ -38,7 +38,7 @@ constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + 256 /*barriers*/ + 2 * 
 constexpr uint32_t kTmemCols = 512;
 
 struct SmemCtl {
-    uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+    uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], bres;
     uint32_t tmem_base;
 };
 
@@ -74,6 +74,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.flags & CONV_F_TMA_OUT) prefetch_tmap(&tmC);
         for (int s = 0; s < kStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
+        mbar_init(&ctl->bres, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(&ctl->tmem_base);
@@ -88,6 +89,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
+            if (p.resident_b) {
+                // Small-K layers are bound by the TMA instruction rate (~1 per 350 cycles per SM), not by
+                // bytes: fetch the whole [block_n x Ktot] weight panel once and keep it in the (otherwise
+                // unused) B stage region; the k loop then issues one TMA per k-block instead of two.
+                mbar_expect_tx(&ctl->bres, (uint32_t)p.resident_b * b_bytes);
+                for (int j = 0; j < p.resident_b; ++j)
+                    tma_load_2d(&tmB, &ctl->bres, sB + j * b_bytes, j * p.kchunk, 0);
+            }
             for (int t = unit0; t < units; t += unit_step) {
                 const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
                 const int m0 = m_blk * kBlockM;
@@ -99,13 +108,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     for (int cc = 0; cc < p.cin_chunks; ++cc) {
                         mbar_wait(&ctl->empty[stage], phase ^ 1);
-                        mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
+                        if (p.debug == 2) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
+                        mbar_expect_tx(&ctl->full[stage], p.resident_b ? a_bytes : a_bytes + b_bytes);
                         if (p.a_mode == 1)
                             tma_load_im2col_4d(&tmA, &ctl->full[stage], sA + stage * kAStageBytes, cc * p.kchunk, bw, bh, img,
                                                (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
                         else
                             tma_load_2d(&tmA, &ctl->full[stage], sA + stage * kAStageBytes, cc * p.kchunk, m0);
-                        if (cs > 1)
+                        if (p.resident_b) {
+                        } else if (cs > 1)
                             tma_load_2d_mc(&tmB, &ctl->full[stage], sB + stage * kBStageBytes + crank * b_rows * p.kchunk * 2,
                                            p.tap_kofs[tap] + cc * p.kchunk, n_blk * p.block_n + crank * b_rows, cmask);
                         else
@@ -122,6 +133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sw = p.kchunk == 64 ? SW_128B : SW_64B;
         const uint32_t sbo = p.kchunk == 64 ? 1024 : 512;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        if (p.resident_b) mbar_wait(&ctl->bres, 0);
         for (int t = unit0; t < units; t += unit_step) {
             mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
@@ -131,12 +143,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(sA + stage * kAStageBytes);
-                    const uint32_t b_addr = smem_u32(sB + stage * kBStageBytes);
+                    uint32_t b_addr = smem_u32(sB + stage * kBStageBytes);
+                    if (p.resident_b) {              // slab of this (tap, channel chunk) inside the resident panel
+                        const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+                        b_addr = smem_u32(sB) + (uint32_t)(p.tap_kofs[tap] / p.kchunk + cc) * b_bytes;
+                    }
                     const int nk = p.kchunk / 16;
                     for (int k = 0; k < nk; ++k) {
                         const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, sbo, sw);
                         const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, sbo, sw);
-                        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                        if (p.debug != 1) umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
                     }
                     if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);      // the slot is free once EVERY CTA has consumed it
                     else umma_commit(&ctl->empty[stage]);

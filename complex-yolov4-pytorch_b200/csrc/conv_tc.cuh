@@ -21,6 +21,8 @@ struct ConvKParams {
     int kchunk, cin_chunks, ntaps;
     int a_mode;                  // 0: A is a plain [M, K] matrix (tiled TMA) ; 1: im2col TMA
     int cluster;                 // CTAs per cluster sharing (multicasting) the weight slabs: 1, 2 or 4
+    int debug;                   // 1: skip MMAs, 2: skip TMA loads (bottleneck experiments)
+    int resident_b;              // >0: number of [block_n x kchunk] weight slabs kept in smem for the whole kernel
     int ab_fmt;                  // 0 fp16, 1 bf16
     // im2col base-pixel space: pixel m -> (img, pi, qi) over Po x Qo ; TMA base = (qi*tstride + lower_w, ...)
     int Po, Qo, tstride, lower_w, lower_h;

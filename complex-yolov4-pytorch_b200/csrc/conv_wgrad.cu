@@ -5,8 +5,8 @@
 // a GEMM whose reduction dimension is the pixel index, so BOTH operands are "MN-major" in shared
 // memory (channels contiguous, pixels strided) -- the UMMA instruction descriptor's a_major/b_major
 // bits select that, and TMA delivers the slabs in exactly the canonical MN-major 128B-swizzle
-// layout: 64-pixel x 64-channel boxes, 8-pixel groups 1024 B apart (SBO), 64-channel column blocks
-// one box (8192 B) apart (LBO).  X goes through the same im2col-mode tensor map as fprop.
+// layout: 128-pixel x 64-channel boxes, 8-pixel groups 1024 B apart (SBO), 64-channel column blocks
+// one box (16 KB) apart (LBO).  X goes through the same im2col-mode tensor map as fprop.
 //
 // Work item = (128 output channels) x (<= 256 input channels) x (one tap) x (one slice of the
 // pixel range); split-K slices add their fp32 partial tile into dw_acc with red.global.add.
@@ -21,12 +21,16 @@
 namespace cy4 {
 using namespace sm100;
 extern int g_wgrad_cluster;      // conv_api.cu (cy4_set_option)
+extern int g_debug;              // 1: skip the MMAs, 2: skip the TMA loads (bottleneck experiments only)
 
-constexpr int kWStages = 4;
+// The TMA unit sustains roughly one bulk-tensor instruction per ~350 cycles per SM regardless of the
+// box size (measured: tools/bottleneck.py), so the boxes are made as large as the
+// 128-byte swizzle span allows: 128 pixels x 64 channels (16 KB).  Two stages of 96 KB.
+constexpr int kWStages = 2;
 constexpr int kWThreads = 192;
-constexpr int kPixBlk = 64;                         // pixels (GEMM K) per pipeline stage
-constexpr int kWAStage = 2 * kPixBlk * 128;         // dY: two 64-channel boxes  = 16 KB
-constexpr int kWBStage = 4 * kPixBlk * 128;         // X : up to four boxes      = 32 KB
+constexpr int kPixBlk = 128;                        // pixels (GEMM K) per pipeline stage
+constexpr int kWAStage = 2 * kPixBlk * 128;         // dY: two 64-channel boxes  = 32 KB
+constexpr int kWBStage = 4 * kPixBlk * 128;         // X : up to four boxes      = 64 KB
 constexpr int kWSmem = kWStages * (kWAStage + kWBStage) + 1024 + 256;
 
 struct WgradParams {
@@ -35,6 +39,7 @@ struct WgradParams {
     int m_tiles, n_tiles, block_n, ntaps, ksplit, kblocks;   // kblocks = ceil(Mpix/64)
     int tpc, tap_groups;         // taps handled by one CTA (accumulators tpc * block_n TMEM columns <= 256)
     int cluster;                 // CTAs per cluster (consecutive m tiles) sharing every X slab through TMA multicast
+    int debug;
     int b_boxes;                 // block_n / 64 (or 1 when the 64B-swizzle N=32 path is used)
     int b_sw64;                  // 1: X has 32 channels, single [64 px x 32 ch] box, 64B swizzle
     int a_matrix;                // 1: X is a plain matrix (tiled TMA), only with ntaps == 1
@@ -96,6 +101,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int m0 = kb * kPixBlk;
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    if (p.debug == 2) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == kWStages) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(&ctl->full[stage], bytes);
                     for (int bx = 0; bx < a_boxes; ++bx)
                         tma_load_2d(&tmDy, &ctl->full[stage], sA + stage * kWAStage + bx * (kPixBlk * 128), m_blk * 128 + bx * 64, m0);
@@ -139,7 +145,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                             const uint64_t ad = make_smem_desc(a_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
                             const uint64_t bd = p.b_sw64 ? make_smem_desc(b_addr + k * 16 * 64, 0, 512, SW_64B)
                                                          : make_smem_desc(b_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
-                            umma_f16(tmem_base + t * p.block_n, ad, bd, idesc, (kb | k) != 0);
+                            if (p.debug != 1) umma_f16(tmem_base + t * p.block_n, ad, bd, idesc, (kb | k) != 0);
                         }
                     }
                     if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);
@@ -210,6 +216,7 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     if (p.ntaps == 9) p.tpc = p.tpc >= 5 ? 5 : (p.tpc >= 3 ? 3 : p.tpc);      // balanced groups: 5+4, 3+3+3, 2+2+2+2+1
     p.tap_groups = (p.ntaps + p.tpc - 1) / p.tpc;
     // pairs of CTAs on consecutive m tiles share (multicast) the X slabs; not for the matrix (stem) mode
+    p.debug = g_debug;
     p.cluster = (g_wgrad_cluster >= 2 && !(d->flags & CY4_CONV_A_MATRIX) && p.m_tiles % 2 == 0) ? 2 : 1;
     const int items = p.m_tiles * p.n_tiles * p.tap_groups;
     p.ksplit = std::max(1, std::min(p.kblocks, (2 * sm_count() + items - 1) / items));

@@ -201,6 +201,30 @@ def test_conv_fp32_output_parity():
         assert (y.cpu() - ref).abs().max().item() <= 1e-3          # measured ~1e-5
 
 
+def test_resident_weight_panel():
+    """Small-K layers keep the whole weight panel in shared memory: same results as the streaming path,
+    checked on shapes with more tiles than SMs (3x3 s1/s2, 1x1, Cin=32, stride-2 dgrad parity classes)."""
+    from cy4 import _lib, convops as co
+    L = _lib.lib()
+    torch.manual_seed(31)
+    for (B, H, W, Cin, Cout, k, stride) in [(4, 152, 152, 64, 64, 3, 1), (4, 152, 152, 32, 64, 3, 2), (8, 152, 152, 64, 64, 1, 1),
+                                             (4, 152, 152, 128, 64, 1, 1)]:
+        pad = (k - 1) // 2
+        x = torch.randn(B, H, W, Cin, device="cuda").half()
+        w = (torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).half()
+        Ho = (H + 2 * pad - k) // stride + 1
+        dy = torch.randn(B, Ho, Ho, Cout, device="cuda").half()
+        wp, wd = co.pack_fprop(w.float()), co.pack_dgrad(w.float())
+        outs = []
+        for res in (1, 0):
+            _lib.check(L.cy4_set_option(b"resident_weights", res))
+            outs.append((co.conv_fwd(x, wp, Cout, k, stride, pad), co.conv_dgrad(dy, wd, H, W, Cin, k, stride, pad)))
+        _lib.check(L.cy4_set_option(b"resident_weights", 1))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        ref = _ref_conv(x, w, stride, pad)
+        assert (outs[0][0].float().cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
 @pytest.mark.parametrize("option,value", [("conv_cluster", 2), ("conv_cluster", 4), ("wgrad_cluster", 2), ("tma_store", 0)])
 def test_conv_variants(option, value):
     """The optional code paths (TMA multicast of the weight / activation slabs across thread-block
