@@ -22,7 +22,7 @@ static int pick_block_n(int cout_pad)
 int g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;
 int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 1;
 int g_debug = 0;
-int g_resident_b = 1;
+int g_resident_b = 0;      // measured slower than streaming on B200 (tools/bottleneck.py); kept as an option
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.

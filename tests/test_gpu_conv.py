@@ -219,7 +219,7 @@ def test_resident_weight_panel():
         for res in (1, 0):
             _lib.check(L.cy4_set_option(b"resident_weights", res))
             outs.append((co.conv_fwd(x, wp, Cout, k, stride, pad), co.conv_dgrad(dy, wd, H, W, Cin, k, stride, pad)))
-        _lib.check(L.cy4_set_option(b"resident_weights", 1))
+        _lib.check(L.cy4_set_option(b"resident_weights", 0))
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
         ref = _ref_conv(x, w, stride, pad)
         assert (outs[0][0].float().cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
