@@ -75,12 +75,23 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     if (g_cluster >= 4 && p.tiles_m >= 8 && p.block_n >= 64) p.cluster = 4;
     // whole weight panel resident in smem when it fits the B stage region (128 KB) and there is one n tile
     p.resident_b = 0;
-    if (g_resident_b && p.tiles_n == 1 && (int64_t)p.block_n * g.w_ktot * 2 <= 4 * 32768 && g.w_ktot % p.kchunk == 0 && p.tiles_m > sm_count()) {
+    if (g_resident_b && p.tiles_n == 1 && (int64_t)p.block_n * g.w_ktot * 2 <= 4 * 32768 && g.w_ktot % p.kchunk == 0 && p.tiles_m > sm_count() && g.ntaps * p.cin_chunks <= 64) {
         p.resident_b = (int)(g.w_ktot / p.kchunk);
         p.cluster = 1;
     }
     rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n / p.cluster, swz, 0);
     if (rc) return rc;
+    // split the 192 KB stage region into as many pipeline slots as fit (at most 12)
+    p.a_stage = 128 * p.kchunk * 2;
+    p.b_stage = (p.block_n * p.kchunk * 2 + 1023) / 1024 * 1024;
+    if (p.resident_b) {
+        const int b_region = (p.resident_b * p.block_n * p.kchunk * 2 + 1023) / 1024 * 1024;
+        p.stages = std::max(2, std::min(12, (4 * 49152 - b_region) / p.a_stage));
+        p.b_stage = 0;
+        // the resident panel sits right after the A slots
+    } else {
+        p.stages = std::max(2, std::min(12, (4 * 49152) / (p.a_stage + p.b_stage)));
+    }
     alignas(64) CUtensorMap tmC = tmB;
     if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {
         // dense fp16 output: epilogue stages 32-row slabs in swizzled smem and TMA-stores them

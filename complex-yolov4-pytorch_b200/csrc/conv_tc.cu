@@ -27,19 +27,22 @@ namespace cy4 {
 using namespace sm100;
 
 constexpr int kBlockM = 128;
-constexpr int kStages = 4;
+constexpr int kStages = 4;                         // stage REGION = 4 x 48 KB; split into p.stages (<= kMaxStages) slots
+constexpr int kMaxStages = 12;
 constexpr int kThreads = 320;                      // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kAStageBytes = kBlockM * 128;        // 16 KB (kchunk 64) ; 8 KB used when kchunk 32
 constexpr int kBStageBytes = 256 * 128;            // 32 KB (block_n 256, kchunk 64)
 constexpr int kMaxStatCh = 1024;                   // per-CTA shared accumulators for the BN statistics
 constexpr int kOutStageBytes = 8 * 32 * 64;        // per epilogue warp: 32 rows x 64 B (32 fp16 columns) slab for the TMA store
 constexpr int kCtlOffset = kStages * (kAStageBytes + kBStageBytes) + kOutStageBytes;
-constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + 256 /*barriers*/ + 2 * kMaxStatCh * 4;
+constexpr int kCtlBytes = 512;                     // barriers, TMEM base, slab table
+constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + kCtlBytes + 2 * kMaxStatCh * 4;
 constexpr uint32_t kTmemCols = 512;
 
 struct SmemCtl {
-    uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], bres;
+    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], bres;
     uint32_t tmem_base;
+    uint16_t slab_of_kb[64];       // resident weight panel: slab index of every k-block (num_kb <= 64 in that mode)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -48,14 +51,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // The TMA -> MMA round trip is ~1.5-2 us; a slot only holds 12..48 KB, so narrow / small-K layers need
+    // many more slots in flight than the 4 that fit for the 128x256x64 tile (measured).
+    const int nst = p.stages;
     uint8_t *sA = smem;
-    uint8_t *sB = smem + kStages * kAStageBytes;
+    uint8_t *sB = smem + nst * p.a_stage;
     uint8_t *sOut = smem + kStages * (kAStageBytes + kBStageBytes);
     SmemCtl *ctl = (SmemCtl *)(smem + kCtlOffset);
-    float *sstat = (float *)(smem + kCtlOffset + 256);     // [2][kMaxStatCh]
+    float *sstat = (float *)(smem + kCtlOffset + kCtlBytes);     // [2][kMaxStatCh]
+    static_assert(sizeof(SmemCtl) <= kCtlBytes, "control block does not fit");
     const bool smem_stats = (p.flags & CONV_F_STATS) && p.tiles_n * p.block_n <= kMaxStatCh;
     if (smem_stats)
         for (int i = threadIdx.x; i < 2 * kMaxStatCh; i += kThreads) sstat[i] = 0.f;
+    if (p.resident_b)
+        for (int kb = threadIdx.x; kb < p.ntaps * p.cin_chunks; kb += kThreads) {
+            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            ctl->slab_of_kb[kb] = (uint16_t)(p.tap_kofs[tap] / p.kchunk + cc);
+        }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Work units: (group of `cluster` consecutive m tiles) x n tile.  The CTAs of a cluster take the m
@@ -72,7 +84,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
         if (p.flags & CONV_F_TMA_OUT) prefetch_tmap(&tmC);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
+        for (int s = 0; s < nst; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
         mbar_init(&ctl->bres, 1);
         fence_barrier_init();
@@ -108,21 +120,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     for (int cc = 0; cc < p.cin_chunks; ++cc) {
                         mbar_wait(&ctl->empty[stage], phase ^ 1);
-                        if (p.debug == 2) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
+                        if (p.debug == 2) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == nst) { stage = 0; phase ^= 1; } continue; }
                         mbar_expect_tx(&ctl->full[stage], p.resident_b ? a_bytes : a_bytes + b_bytes);
                         if (p.a_mode == 1)
-                            tma_load_im2col_4d(&tmA, &ctl->full[stage], sA + stage * kAStageBytes, cc * p.kchunk, bw, bh, img,
+                            tma_load_im2col_4d(&tmA, &ctl->full[stage], sA + stage * p.a_stage, cc * p.kchunk, bw, bh, img,
                                                (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
                         else
-                            tma_load_2d(&tmA, &ctl->full[stage], sA + stage * kAStageBytes, cc * p.kchunk, m0);
+                            tma_load_2d(&tmA, &ctl->full[stage], sA + stage * p.a_stage, cc * p.kchunk, m0);
                         if (p.resident_b) {
                         } else if (cs > 1)
-                            tma_load_2d_mc(&tmB, &ctl->full[stage], sB + stage * kBStageBytes + crank * b_rows * p.kchunk * 2,
+                            tma_load_2d_mc(&tmB, &ctl->full[stage], sB + stage * p.b_stage + crank * b_rows * p.kchunk * 2,
                                            p.tap_kofs[tap] + cc * p.kchunk, n_blk * p.block_n + crank * b_rows, cmask);
                         else
-                            tma_load_2d(&tmB, &ctl->full[stage], sB + stage * kBStageBytes, p.tap_kofs[tap] + cc * p.kchunk,
+                            tma_load_2d(&tmB, &ctl->full[stage], sB + stage * p.b_stage, p.tap_kofs[tap] + cc * p.kchunk,
                                         n_blk * p.block_n);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -142,12 +154,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&ctl->full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(sA + stage * kAStageBytes);
-                    uint32_t b_addr = smem_u32(sB + stage * kBStageBytes);
-                    if (p.resident_b) {              // slab of this (tap, channel chunk) inside the resident panel
-                        const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
-                        b_addr = smem_u32(sB) + (uint32_t)(p.tap_kofs[tap] / p.kchunk + cc) * b_bytes;
-                    }
+                    const uint32_t a_addr = smem_u32(sA + stage * p.a_stage);
+                    uint32_t b_addr = smem_u32(sB + stage * p.b_stage);
+                    if (p.resident_b) b_addr = smem_u32(sB) + (uint32_t)ctl->slab_of_kb[kb] * b_bytes;   // slab inside the resident panel
                     const int nk = p.kchunk / 16;
                     for (int k = 0; k < nk; ++k) {
                         const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, sbo, sw);
@@ -159,7 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
