@@ -81,6 +81,9 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     }
     rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n / p.cluster, swz, 0);
     if (rc) return rc;
+    // output slabs per epilogue warp: 4 for narrow tiles (epilogue-bound, TMA-store latency), else 1
+    p.slab_bufs = (p.block_n <= 64 && !p.resident_b) ? 4 : (p.block_n <= 128 && !p.resident_b ? 2 : 1);
+    const int slab_extra = (p.slab_bufs - 1) * 8 * 32 * 64;
     // split the 192 KB stage region into as many pipeline slots as fit (at most 12)
     p.a_stage = 128 * p.kchunk * 2;
     p.b_stage = (p.block_n * p.kchunk * 2 + 1023) / 1024 * 1024;
@@ -90,7 +93,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
         p.b_stage = 0;
         // the resident panel sits right after the A slots
     } else {
-        p.stages = std::max(2, std::min(12, (4 * 49152) / (p.a_stage + p.b_stage)));
+        p.stages = std::max(2, std::min(12, (4 * 49152 - slab_extra) / (p.a_stage + p.b_stage)));
     }
     alignas(64) CUtensorMap tmC = tmB;
     if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {

@@ -178,6 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int group = (warp - 2) >> 2;            // group g owns accumulator stage g
         const int acc = group; uint32_t acc_phase = 0;
         int seq = 0;
+        int slab_i = 0;                               // rotating output slab of this warp
         for (int t = unit0; t < units; t += unit_step, ++seq) {
             if ((seq & 1) != group) continue;
             const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
@@ -206,11 +207,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // fp16 slab [32 rows][cw columns] of this warp in swizzled smem, then one TMA store
                     // (coalesced, clipped to M rows by the tensor map).  cw = 64 (128B swizzle) or 32 (64B).
                     // (32 columns = 64-byte rows, 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3)
-                    uint8_t *slab = sOut + (warp - 2) * (32 * 64);
+                    // Narrow layers are bound by the TMA-store round trip of this slab, so they rotate through
+                    // up to 4 slabs per warp (extra slabs live at the tail of the 192 KB stage region).
+                    uint8_t *slab = (slab_i == 0 ? sOut : smem + kStages * (kAStageBytes + kBStageBytes) - slab_i * kOutStageBytes) + (warp - 2) * (32 * 64);
                     const int cw = 32;
                     const int sub = 0;
-                    if (lane == 0) tma_store_wait_read();            // the previous store must have read the slab
+                    if (lane == 0) tma_store_wait_read_n(p.slab_bufs - 1);   // the store that used this slab has read it
                     __syncwarp();
+                    if (++slab_i == p.slab_bufs) slab_i = 0;
                     const int rowbytes = cw * 2;
                     const int xr = (lane >> 1) & 3;
 #pragma unroll

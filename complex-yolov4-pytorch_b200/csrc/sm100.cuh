@@ -121,6 +121,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// wait until at most `pending` (0, 1 or 3) of this thread's bulk store groups are still reading shared memory
+__device__ __forceinline__ void tma_store_wait_read_n(int pending)
+{
+    if (pending >= 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+    else if (pending >= 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------
