@@ -142,8 +142,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n, p.ab_fmt, 0, 0);
-        const uint32_t sw = p.kchunk == 64 ? SW_128B : SW_64B;
-        const uint32_t sbo = p.kchunk == 64 ? 1024 : 512;
+        const uint32_t dhi = smem_desc_hi(p.kchunk == 64 ? 1024 : 512, p.kchunk == 64 ? SW_128B : SW_64B);
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         if (p.resident_b) mbar_wait(&ctl->bres, 0);
         for (int t = unit0; t < units; t += unit_step) {
@@ -154,14 +154,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&ctl->full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(sA + stage * p.a_stage);
-                    uint32_t b_addr = smem_u32(sB + stage * p.b_stage);
-                    if (p.resident_b) b_addr = smem_u32(sB) + (uint32_t)ctl->slab_of_kb[kb] * b_bytes;   // slab inside the resident panel
-                    const int nk = p.kchunk / 16;
-                    for (int k = 0; k < nk; ++k) {
-                        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, sbo, sw);
-                        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, sbo, sw);
-                        if (p.debug != 1) umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                    uint32_t b_addr = b_base + stage * p.b_stage;
+                    if (p.resident_b) b_addr = b_base + (uint32_t)ctl->slab_of_kb[kb] * b_bytes;   // slab inside the resident panel
+                    const uint32_t a_lo = smem_desc_lo(a_base + stage * p.a_stage, 16);
+                    const uint32_t b_lo = smem_desc_lo(b_addr, 16);
+                    if (p.debug != 1) {
+                        umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, kb != 0);
+                        umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1);       // +32 bytes of K per MMA
+                        if (p.kchunk == 64) {
+                            umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1);
+                            umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1);
+                        }
                     }
                     if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);      // the slot is free once EVERY CTA has consumed it
                     else umma_commit(&ctl->empty[stage]);

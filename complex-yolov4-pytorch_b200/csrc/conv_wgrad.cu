@@ -130,22 +130,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             }
         } else if (warp == 1) {
             const uint32_t idesc = make_idesc_f16(128, p.block_n, 0, 1, 1);       // both operands MN-major
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            const uint32_t a_hi = smem_desc_hi(1024, SW_128B);
+            const uint32_t b_hi = p.b_sw64 ? smem_desc_hi(512, SW_64B) : smem_desc_hi(1024, SW_128B);
+            const uint32_t b_kstep = p.b_sw64 ? (16 * 64 / 16) : (16 * 128 / 16);          // 16 pixel rows, in 16-byte units
+            const uint32_t b_tap_bytes = p.b_sw64 ? kPixBlk * 64 : p.b_boxes * kPixBlk * 128;
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&ctl->full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(sA + stage * kWAStage);
-                    const uint32_t b_tap_bytes = p.b_sw64 ? kPixBlk * 64 : p.b_boxes * kPixBlk * 128;
+                    // descriptors as (lo, hi) halves: hi is a loop constant, lo advances by 16 pixel rows per MMA
+                    const uint32_t a_lo0 = smem_desc_lo(a_base + stage * kWAStage, kPixBlk * 128);
                     for (int t = 0; t < ntap; ++t) {
-                        const uint32_t b_addr = smem_u32(sB + stage * kWBStage) + t * b_tap_bytes;
+                        const uint32_t b_addr = b_base + stage * kWBStage + t * b_tap_bytes;
+                        const uint32_t b_lo0 = p.b_sw64 ? smem_desc_lo(b_addr, 0) : smem_desc_lo(b_addr, kPixBlk * 128);
+                        const uint32_t d_t = tmem_base + t * p.block_n;
+                        if (p.debug != 1) {
 #pragma unroll
-                        for (int k = 0; k < kPixBlk / 16; ++k) {
-                            // 16 pixels = two 8-row groups: advance 16 rows of 128 B (64 B in the 64B-swizzle case)
-                            const uint64_t ad = make_smem_desc(a_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
-                            const uint64_t bd = p.b_sw64 ? make_smem_desc(b_addr + k * 16 * 64, 0, 512, SW_64B)
-                                                         : make_smem_desc(b_addr + k * 16 * 128, kPixBlk * 128, 1024, SW_128B);
-                            if (p.debug != 1) umma_f16(tmem_base + t * p.block_n, ad, bd, idesc, (kb | k) != 0);
+                            for (int k = 0; k < kPixBlk / 16; ++k)
+                                umma_f16_lohi(d_t, a_lo0 + k * (16 * 128 / 16), a_hi, b_lo0 + k * b_kstep, b_hi, idesc, (kb | k) != 0);
                         }
                     }
                     if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);

@@ -155,6 +155,30 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with the descriptors given as (lo, hi) 32-bit halves: the single issuing thread is the
+// critical path of the whole kernel (one thread retires ~1 dependent instruction per 4-6 cycles), so the
+// per-MMA work is reduced to one 32-bit add per operand: hi halves are loop constants, lo = base + 2*k.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t swizzle)
+{
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((swizzle & 7u) << 29);     // bits [32,46) SBO, [46,48) version, [61,64) swizzle
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes)
+{
+    return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
