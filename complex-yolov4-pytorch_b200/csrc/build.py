@@ -18,6 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "--expt-extended-lambda", "--expt-relaxed-constexpr",
           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-DCY4_BUILD"]
+COMMON += os.environ.get("CY4_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DCY4_PROBE for tools/probe_pipeline.py
 PER_FILE = {
     "rgiou.cu": ["--fmad=false"],
     "yolo_head.cu": ["--fmad=false"],

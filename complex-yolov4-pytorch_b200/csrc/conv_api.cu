@@ -22,6 +22,7 @@ static int pick_block_n(int cout_pad)
 int g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;
 int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 1;
 int g_debug = 0;
+int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disables the packing)
 int g_resident_b = 0;      // measured slower than streaming on B200 (tools/bottleneck.py); kept as an option
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 
@@ -75,6 +76,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     if (g_cluster >= 4 && p.tiles_m >= 8 && p.block_n >= 64) p.cluster = 4;
     // whole weight panel resident in smem when it fits the B stage region (128 KB) and there is one n tile
     p.resident_b = 0;
+    p.kps = 1;
     if (g_resident_b && p.tiles_n == 1 && (int64_t)p.block_n * g.w_ktot * 2 <= 4 * 32768 && g.w_ktot % p.kchunk == 0 && p.tiles_m > sm_count() && g.ntaps * p.cin_chunks <= 64) {
         p.resident_b = (int)(g.w_ktot / p.kchunk);
         p.cluster = 1;
@@ -93,7 +95,12 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
         p.b_stage = 0;
         // the resident panel sits right after the A slots
     } else {
-        p.stages = std::max(2, std::min(12, (4 * 49152 - slab_extra) / (p.a_stage + p.b_stage)));
+        // The full/empty barrier round trip costs ~450 cycles per slot whatever the slot holds (measured with
+        // loads and MMAs disabled), far more than the MMAs of one narrow k-block: pack several k-blocks per slot
+        // while a slot stays <= 48 KB.
+        const int num_kb = g.ntaps * p.cin_chunks;
+        p.kps = (p.cluster == 1 && g_kps_max > 1) ? std::max(1, std::min(std::min(g_kps_max, num_kb), 49152 / (p.a_stage + p.b_stage))) : 1;
+        p.stages = std::max(2, std::min(12, (4 * 49152 - slab_extra) / (p.kps * (p.a_stage + p.b_stage))));
     }
     alignas(64) CUtensorMap tmC = tmB;
     if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {
@@ -257,6 +264,7 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
     if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
     if (!strcmp(name, "resident_weights")) { g_resident_b = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "kblocks_per_slot")) { g_kps_max = value < 1 ? 1 : (value > 8 ? 8 : value); return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage
     set_error("cy4_set_option: unknown option %s", name);
     return -1;

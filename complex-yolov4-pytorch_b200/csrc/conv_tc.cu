@@ -45,6 +45,39 @@ struct SmemCtl {
     uint16_t slab_of_kb[64];       // resident weight panel: slab index of every k-block (num_kb <= 64 in that mode)
 };
 
+// Cycle probes of the two single-thread loops (compile with -DCY4_PROBE; tools/probe_pipeline.py). Off in the product build.
+#ifdef CY4_PROBE
+__device__ unsigned long long g_probe[16];
+#define PROBE_DECL unsigned long long pr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_ = 0
+#define PROBE_T0 pt_ = clock64()
+#define PROBE_ACC(i) do { long long n_ = clock64(); pr_[i] += (unsigned long long)(n_ - pt_); pt_ = n_; } while (0)
+#define PROBE_CNT(i) pr_[i] += 1
+#define PROBE_FLUSH(base) do { if (lane == 0 && blockIdx.x == 0) for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_probe[(base) + i_], pr_[i_]); } while (0)
+#define PPROBE_DECL PROBE_DECL
+#define PPROBE_T0 PROBE_T0
+#define PPROBE_ACC(i) PROBE_ACC(i)
+#define PPROBE_CNT(i) PROBE_CNT(i)
+#define PPROBE_FLUSH(base) PROBE_FLUSH(base)
+#else
+#define PROBE_DECL
+#define PROBE_T0
+#define PROBE_ACC(i)
+#define PROBE_CNT(i)
+#define PROBE_FLUSH(base)
+#define PPROBE_DECL
+#define PPROBE_T0
+#define PPROBE_ACC(i)
+#define PPROBE_CNT(i)
+#define PPROBE_FLUSH(base)
+#endif
+
+// the bottleneck-experiment switches (cy4_set_option "debug") only exist in -DCY4_PROBE builds
+#ifdef CY4_PROBE
+#define CY4_DBG (p.debug)
+#else
+#define CY4_DBG 0
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvKParams p)
@@ -53,9 +86,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // The TMA -> MMA round trip is ~1.5-2 us; a slot only holds 12..48 KB, so narrow / small-K layers need
     // many more slots in flight than the 4 that fit for the 128x256x64 tile (measured).
-    const int nst = p.stages;
+    const int nst = p.stages, kps = p.kps;
     uint8_t *sA = smem;
-    uint8_t *sB = smem + nst * p.a_stage;
+    uint8_t *sB = smem + nst * kps * p.a_stage;
     uint8_t *sOut = smem + kStages * (kAStageBytes + kBStageBytes);
     SmemCtl *ctl = (SmemCtl *)(smem + kCtlOffset);
     float *sstat = (float *)(smem + kCtlOffset + kCtlBytes);     // [2][kMaxStatCh]
@@ -69,7 +102,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ctl->slab_of_kb[kb] = (uint16_t)(p.tap_kofs[tap] / p.kchunk + cc);
         }
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps
+    // the single-thread loops' operands in uniform registers (no R2UR broadcast loops around TMA / MMA issue)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // Work units: (group of `cluster` consecutive m tiles) x n tile.  The CTAs of a cluster take the m
     // tiles of one group, walk the same k loop and share every weight slab through TMA multicast.
     const int cs = p.cluster;
@@ -94,11 +129,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (cs > 1) cluster_sync_all();          // peers' barriers are initialised before any multicast targets them
     tc_fence_after();
-    const uint32_t tmem_base = ctl->tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
+            PPROBE_DECL;
             int stage = 0; uint32_t phase = 0;
             const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
             if (p.resident_b) {
@@ -117,27 +153,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rem = m0 - img * (p.Po * p.Qo);
                 const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
                 const int bw = qi * p.tstride + p.lower_w, bh = pi * p.tstride + p.lower_h;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                        mbar_wait(&ctl->empty[stage], phase ^ 1);
-                        if (p.debug == 2) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == nst) { stage = 0; phase ^= 1; } continue; }
-                        mbar_expect_tx(&ctl->full[stage], p.resident_b ? a_bytes : a_bytes + b_bytes);
+                int tap = 0, cc = 0;
+                for (int g0 = 0; g0 < num_kb; g0 += kps) {
+                    const int cnt = min(kps, num_kb - g0);         // k-blocks of this slot
+                    PPROBE_T0;
+                    mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    PPROBE_ACC(0);
+                    if (CY4_DBG == 2 || CY4_DBG == 3 || CY4_DBG == 6) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == nst) { stage = 0; phase ^= 1; } continue; }
+                    mbar_expect_tx(&ctl->full[stage], (uint32_t)cnt * (p.resident_b ? a_bytes : a_bytes + b_bytes));
+                    for (int j = 0; j < cnt; ++j) {
+                        const int slot = stage * kps + j;
                         if (p.a_mode == 1)
-                            tma_load_im2col_4d(&tmA, &ctl->full[stage], sA + stage * p.a_stage, cc * p.kchunk, bw, bh, img,
+                            tma_load_im2col_4d(&tmA, &ctl->full[stage], sA + slot * p.a_stage, cc * p.kchunk, bw, bh, img,
                                                (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
                         else
-                            tma_load_2d(&tmA, &ctl->full[stage], sA + stage * p.a_stage, cc * p.kchunk, m0);
+                            tma_load_2d(&tmA, &ctl->full[stage], sA + slot * p.a_stage, cc * p.kchunk, m0);
                         if (p.resident_b) {
                         } else if (cs > 1)
-                            tma_load_2d_mc(&tmB, &ctl->full[stage], sB + stage * p.b_stage + crank * b_rows * p.kchunk * 2,
+                            tma_load_2d_mc(&tmB, &ctl->full[stage], sB + slot * p.b_stage + crank * b_rows * p.kchunk * 2,
                                            p.tap_kofs[tap] + cc * p.kchunk, n_blk * p.block_n + crank * b_rows, cmask);
                         else
-                            tma_load_2d(&tmB, &ctl->full[stage], sB + stage * p.b_stage, p.tap_kofs[tap] + cc * p.kchunk,
+                            tma_load_2d(&tmB, &ctl->full[stage], sB + slot * p.b_stage, p.tap_kofs[tap] + cc * p.kchunk,
                                         n_blk * p.block_n);
-                        if (++stage == nst) { stage = 0; phase ^= 1; }
+                        if (++cc == p.cin_chunks) { cc = 0; ++tap; }
                     }
+                    PPROBE_ACC(1);
+                    PPROBE_CNT(2);
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
             }
+            PPROBE_FLUSH(8);
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
@@ -146,35 +191,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         if (p.resident_b) mbar_wait(&ctl->bres, 0);
+        PROBE_DECL;
         for (int t = unit0; t < units; t += unit_step) {
+            PROBE_T0;
             mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
+            PROBE_ACC(0);
             const uint32_t d_tmem = tmem_base + acc * p.block_n;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int g0 = 0; g0 < num_kb; g0 += kps) {
+                const int cnt = min(kps, num_kb - g0);
+                PROBE_T0;
                 mbar_wait(&ctl->full[stage], phase);
+                PROBE_ACC(1);
                 tc_fence_after();
-                if (lane == 0) {
-                    uint32_t b_addr = b_base + stage * p.b_stage;
-                    if (p.resident_b) b_addr = b_base + (uint32_t)ctl->slab_of_kb[kb] * b_bytes;   // slab inside the resident panel
-                    const uint32_t a_lo = smem_desc_lo(a_base + stage * p.a_stage, 16);
-                    const uint32_t b_lo = smem_desc_lo(b_addr, 16);
-                    if (p.debug != 1) {
-                        umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, kb != 0);
-                        umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1);       // +32 bytes of K per MMA
-                        if (p.kchunk == 64) {
-                            umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1);
-                            umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1);
+                PROBE_ACC(2);
+                if (elect_one()) {
+                    for (int j = 0; j < cnt; ++j) {
+                        const int kb = g0 + j, slot = stage * kps + j;
+                        uint32_t b_addr = b_base + slot * p.b_stage;
+                        if (p.resident_b) b_addr = b_base + (uint32_t)ctl->slab_of_kb[kb] * b_bytes;   // slab inside the resident panel
+                        const uint32_t a_lo = smem_desc_lo(a_base + slot * p.a_stage, 16);
+                        const uint32_t b_lo = smem_desc_lo(b_addr, 16);
+                        if (CY4_DBG != 1 && CY4_DBG != 3 && CY4_DBG != 6) {
+                            umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, kb != 0);
+                            umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1);       // +32 bytes of K per MMA
+                            if (p.kchunk == 64) {
+                                umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1);
+                                umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1);
+                            }
                         }
                     }
-                    if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);      // the slot is free once EVERY CTA has consumed it
+                    PROBE_ACC(3);
+                    if (CY4_DBG == 6) mbar_arrive(&ctl->empty[stage]);             // experiment: plain arrive instead of the commit
+                    else if (cs > 1) umma_commit_mc(&ctl->empty[stage], cmask);    // the slot is free once EVERY CTA has consumed it
                     else umma_commit(&ctl->empty[stage]);
-                    if (kb == num_kb - 1) umma_commit(&ctl->tmem_full[acc]);
+                    if (g0 + cnt == num_kb) umma_commit(&ctl->tmem_full[acc]);
+                    PROBE_ACC(4);
                 }
                 __syncwarp();
+                PROBE_ACC(5);
+                PROBE_CNT(6);
                 if (++stage == nst) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        PROBE_FLUSH(0);
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9)
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) are this warp's
@@ -206,7 +267,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                if (p.flags & CONV_F_TMA_OUT) {
+                if (CY4_DBG == 4 || CY4_DBG == 5) {
+                    if (CY4_DBG == 5 && f[0] == 12345.678f) ((float *)p.y)[0] = f[1];      // keep the TMEM load alive, store nothing
+                } else if (p.flags & CONV_F_TMA_OUT) {
                     // fp16 slab [32 rows][cw columns] of this warp in swizzled smem, then one TMA store
                     // (coalesced, clipped to M rows by the tensor map).  cw = 64 (128B swizzle) or 32 (64B).
                     // (32 columns = 64-byte rows, 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3)
@@ -424,3 +487,13 @@ int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtenso
 }
 
 }  // namespace cy4
+
+#ifdef CY4_PROBE
+extern "C" __attribute__((visibility("default"))) int cy4_probe_read(unsigned long long *out16)
+{
+    cudaDeviceSynchronize();
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out16, cy4::g_probe, sizeof(z)) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(cy4::g_probe, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif

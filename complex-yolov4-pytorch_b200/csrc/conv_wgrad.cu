@@ -54,6 +54,12 @@ struct WCtl {
     uint32_t tmem_base;
 };
 
+#ifdef CY4_PROBE
+#define CY4_WDBG (p.debug)
+#else
+#define CY4_WDBG 0
+#endif
+
 __global__ void __launch_bounds__(kWThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WgradParams p)
 {
@@ -62,7 +68,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     uint8_t *sA = smem;
     uint8_t *sB = smem + kWStages * kWAStage;
     WCtl *ctl = (WCtl *)(smem + kWStages * (kWAStage + kWBStage));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (shuffled warp index / TMEM base: keeps the issue loops' operands in uniform registers, see conv_tc.cu)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     // decode the work item; the CTAs of a cluster differ only in the m tile
     const int cs = p.cluster;
@@ -89,11 +96,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     __syncthreads();
     if (cs > 1) cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = ctl->tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
     if (nkb > 0) {
         if (warp == 0) {
-            if (lane == 0) {
+            if (elect_one()) {
                 const int a_boxes = (m_blk * 128 + 64 < p.Cout) ? 2 : 1;       // skip a fully out-of-range box
                 const uint32_t b_tap_bytes = p.b_sw64 ? kPixBlk * 64 : p.b_boxes * kPixBlk * 128;
                 const uint32_t bytes = a_boxes * kPixBlk * 128 + ntap * b_tap_bytes;
@@ -101,7 +108,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int m0 = kb * kPixBlk;
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
-                    if (p.debug == 2) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == kWStages) { stage = 0; phase ^= 1; } continue; }
+                    if (CY4_WDBG == 2) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == kWStages) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(&ctl->full[stage], bytes);
                     for (int bx = 0; bx < a_boxes; ++bx)
                         tma_load_2d(&tmDy, &ctl->full[stage], sA + stage * kWAStage + bx * (kPixBlk * 128), m_blk * 128 + bx * 64, m0);
@@ -139,14 +146,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&ctl->full[stage], phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     // descriptors as (lo, hi) halves: hi is a loop constant, lo advances by 16 pixel rows per MMA
                     const uint32_t a_lo0 = smem_desc_lo(a_base + stage * kWAStage, kPixBlk * 128);
                     for (int t = 0; t < ntap; ++t) {
                         const uint32_t b_addr = b_base + stage * kWBStage + t * b_tap_bytes;
                         const uint32_t b_lo0 = p.b_sw64 ? smem_desc_lo(b_addr, 0) : smem_desc_lo(b_addr, kPixBlk * 128);
                         const uint32_t d_t = tmem_base + t * p.block_n;
-                        if (p.debug != 1) {
+                        if (CY4_WDBG != 1) {
 #pragma unroll
                             for (int k = 0; k < kPixBlk / 16; ++k)
                                 umma_f16_lohi(d_t, a_lo0 + k * (16 * 128 / 16), a_hi, b_lo0 + k * b_kstep, b_hi, idesc, (kb | k) != 0);
