@@ -341,6 +341,9 @@ def main():
     ap.add_argument("--cfg", default="complex_yolov4")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--cuda-graph", dest="cuda_graph", type=int, default=0, help="replay the fwd/bwd launch sequences as CUDA graphs")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT",
+                    help="cy4_set_option(NAME, INT) before the run (kernel experiments, e.g. conv_cluster=2); recorded in config")
+    ap.add_argument("--no-roofline", dest="no_roofline", action="store_true", help="skip the per-launch roofline pass (quick A/B runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     res = run_reference(args) if args.impl == "reference" else run_ours(args)

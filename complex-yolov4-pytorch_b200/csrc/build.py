@@ -12,8 +12,10 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OUT = os.path.join(HERE, "libcy4.so")
-OBJ = os.path.join(HERE, "build")
+# CY4_LIB_NAME / CY4_EXTRA_NVCC_FLAGS: side builds for experiments (e.g. libcy4_probe.so with -DCY4_PROBE);
+# the product is always libcy4.so with the default flags.
+OUT = os.path.join(HERE, os.environ.get("CY4_LIB_NAME", "libcy4.so"))
+OBJ = os.path.join(HERE, "build" if OUT.endswith("libcy4.so") else "build_" + os.path.basename(OUT).split(".")[0])
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "--expt-extended-lambda", "--expt-relaxed-constexpr",

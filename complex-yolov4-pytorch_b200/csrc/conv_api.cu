@@ -23,7 +23,6 @@ int g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;
 int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 1;
 int g_debug = 0;
 int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disables the packing)
-int g_resident_b = 0;      // measured slower than streaming on B200 (tools/bottleneck.py); kept as an option
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
@@ -74,34 +73,20 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     // clusters of 2 CTAs share each weight slab through TMA multicast (halves the L2 -> SM weight traffic)
     p.cluster = (p.tiles_m >= 2 && g_cluster >= 2) ? 2 : 1;
     if (g_cluster >= 4 && p.tiles_m >= 8 && p.block_n >= 64) p.cluster = 4;
-    // whole weight panel resident in smem when it fits the B stage region (128 KB) and there is one n tile
-    p.resident_b = 0;
-    p.kps = 1;
-    if (g_resident_b && p.tiles_n == 1 && (int64_t)p.block_n * g.w_ktot * 2 <= 4 * 32768 && g.w_ktot % p.kchunk == 0 && p.tiles_m > sm_count() && g.ntaps * p.cin_chunks <= 64) {
-        p.resident_b = (int)(g.w_ktot / p.kchunk);
-        p.cluster = 1;
-    }
     rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n / p.cluster, swz, 0);
     if (rc) return rc;
     // output slabs per epilogue warp: 4 for narrow tiles (epilogue-bound, TMA-store latency), else 1
-    p.slab_bufs = (p.block_n <= 64 && !p.resident_b) ? 4 : (p.block_n <= 128 && !p.resident_b ? 2 : 1);
+    p.slab_bufs = p.block_n <= 64 ? 4 : (p.block_n <= 128 ? 2 : 1);
     const int slab_extra = (p.slab_bufs - 1) * 8 * 32 * 64;
     // split the 192 KB stage region into as many pipeline slots as fit (at most 12)
     p.a_stage = 128 * p.kchunk * 2;
     p.b_stage = (p.block_n * p.kchunk * 2 + 1023) / 1024 * 1024;
-    if (p.resident_b) {
-        const int b_region = (p.resident_b * p.block_n * p.kchunk * 2 + 1023) / 1024 * 1024;
-        p.stages = std::max(2, std::min(12, (4 * 49152 - b_region) / p.a_stage));
-        p.b_stage = 0;
-        // the resident panel sits right after the A slots
-    } else {
-        // The full/empty barrier round trip costs ~450 cycles per slot whatever the slot holds (measured with
-        // loads and MMAs disabled), far more than the MMAs of one narrow k-block: pack several k-blocks per slot
-        // while a slot stays <= 48 KB.
-        const int num_kb = g.ntaps * p.cin_chunks;
-        p.kps = (p.cluster == 1 && g_kps_max > 1) ? std::max(1, std::min(std::min(g_kps_max, num_kb), 49152 / (p.a_stage + p.b_stage))) : 1;
-        p.stages = std::max(2, std::min(12, (4 * 49152 - slab_extra) / (p.kps * (p.a_stage + p.b_stage))));
-    }
+    // Every slot costs the issue threads a barrier round trip and a commit (~250 cycles, tools/probe_pipeline.py),
+    // more than the MMAs of one narrow k-block (128 cycles at N = 64): pack several k-blocks per slot while a
+    // slot stays <= 48 KB.
+    const int num_kb = g.ntaps * p.cin_chunks;
+    p.kps = (p.cluster == 1 && g_kps_max > 1) ? std::max(1, std::min(std::min(g_kps_max, num_kb), 49152 / (p.a_stage + p.b_stage))) : 1;
+    p.stages = std::max(2, std::min(12, (4 * 49152 - slab_extra) / (p.kps * (p.a_stage + p.b_stage))));
     alignas(64) CUtensorMap tmC = tmB;
     if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {
         // dense fp16 output: epilogue stages 32-row slabs in swizzled smem and TMA-stores them
@@ -263,7 +248,6 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "conv_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2 || value == 4, "conv_cluster must be 1, 2 or 4"); g_cluster = value; return 0; }
     if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
     if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
-    if (!strcmp(name, "resident_weights")) { g_resident_b = value ? 1 : 0; return 0; }
     if (!strcmp(name, "kblocks_per_slot")) { g_kps_max = value < 1 ? 1 : (value > 8 ? 8 : value); return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage
     set_error("cy4_set_option: unknown option %s", name);

@@ -40,9 +40,8 @@ constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + kCtlBytes + 2 * kMaxSta
 constexpr uint32_t kTmemCols = 512;
 
 struct SmemCtl {
-    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], bres;
+    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
-    uint16_t slab_of_kb[64];       // resident weight panel: slab index of every k-block (num_kb <= 64 in that mode)
 };
 
 // Cycle probes of the two single-thread loops (compile with -DCY4_PROBE; tools/probe_pipeline.py). Off in the product build.
@@ -96,11 +95,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool smem_stats = (p.flags & CONV_F_STATS) && p.tiles_n * p.block_n <= kMaxStatCh;
     if (smem_stats)
         for (int i = threadIdx.x; i < 2 * kMaxStatCh; i += kThreads) sstat[i] = 0.f;
-    if (p.resident_b)
-        for (int kb = threadIdx.x; kb < p.ntaps * p.cin_chunks; kb += kThreads) {
-            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
-            ctl->slab_of_kb[kb] = (uint16_t)(p.tap_kofs[tap] / p.kchunk + cc);
-        }
 
     // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps
     // the single-thread loops' operands in uniform registers (no R2UR broadcast loops around TMA / MMA issue)
@@ -121,7 +115,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.flags & CONV_F_TMA_OUT) prefetch_tmap(&tmC);
         for (int s = 0; s < nst; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
-        mbar_init(&ctl->bres, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(&ctl->tmem_base);
@@ -137,14 +130,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             PPROBE_DECL;
             int stage = 0; uint32_t phase = 0;
             const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
-            if (p.resident_b) {
-                // Small-K layers are bound by the TMA instruction rate (~1 per 350 cycles per SM), not by
-                // bytes: fetch the whole [block_n x Ktot] weight panel once and keep it in the (otherwise
-                // unused) B stage region; the k loop then issues one TMA per k-block instead of two.
-                mbar_expect_tx(&ctl->bres, (uint32_t)p.resident_b * b_bytes);
-                for (int j = 0; j < p.resident_b; ++j)
-                    tma_load_2d(&tmB, &ctl->bres, sB + j * b_bytes, j * p.kchunk, 0);
-            }
             for (int t = unit0; t < units; t += unit_step) {
                 const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
                 const int m0 = m_blk * kBlockM;
@@ -160,7 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     PPROBE_ACC(0);
                     if (CY4_DBG == 2 || CY4_DBG == 3 || CY4_DBG == 6) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == nst) { stage = 0; phase ^= 1; } continue; }
-                    mbar_expect_tx(&ctl->full[stage], (uint32_t)cnt * (p.resident_b ? a_bytes : a_bytes + b_bytes));
+                    mbar_expect_tx(&ctl->full[stage], (uint32_t)cnt * (a_bytes + b_bytes));
                     for (int j = 0; j < cnt; ++j) {
                         const int slot = stage * kps + j;
                         if (p.a_mode == 1)
@@ -168,8 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
                         else
                             tma_load_2d(&tmA, &ctl->full[stage], sA + slot * p.a_stage, cc * p.kchunk, m0);
-                        if (p.resident_b) {
-                        } else if (cs > 1)
+                        if (cs > 1)
                             tma_load_2d_mc(&tmB, &ctl->full[stage], sB + slot * p.b_stage + crank * b_rows * p.kchunk * 2,
                                            p.tap_kofs[tap] + cc * p.kchunk, n_blk * p.block_n + crank * b_rows, cmask);
                         else
@@ -188,9 +172,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n, p.ab_fmt, 0, 0);
         const uint32_t dhi = smem_desc_hi(p.kchunk == 64 ? 1024 : 512, p.kchunk == 64 ? SW_128B : SW_64B);
-        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA), 16), b_lo0 = smem_desc_lo(smem_u32(sB), 16);
+        const uint32_t a_step = (uint32_t)p.a_stage >> 4, b_step = (uint32_t)p.b_stage >> 4;
+        const bool k64 = p.kchunk == 64;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        if (p.resident_b) mbar_wait(&ctl->bres, 0);
         PROBE_DECL;
         for (int t = unit0; t < units; t += unit_step) {
             PROBE_T0;
@@ -206,16 +191,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 PROBE_ACC(2);
                 if (elect_one()) {
-                    for (int j = 0; j < cnt; ++j) {
-                        const int kb = g0 + j, slot = stage * kps + j;
-                        uint32_t b_addr = b_base + slot * p.b_stage;
-                        if (p.resident_b) b_addr = b_base + (uint32_t)ctl->slab_of_kb[kb] * b_bytes;   // slab inside the resident panel
-                        const uint32_t a_lo = smem_desc_lo(a_base + slot * p.a_stage, 16);
-                        const uint32_t b_lo = smem_desc_lo(b_addr, 16);
+                    // descriptor low words advance by whole slots (addresses are 1024-aligned and < 256 KB, so the
+                    // 14-bit address field never carries): one multiply-add per operand per k-block
+                    uint32_t a_lo = a_lo0 + (uint32_t)(stage * kps) * a_step, b_lo = b_lo0 + (uint32_t)(stage * kps) * b_step;
+                    for (int j = 0; j < cnt; ++j, a_lo += a_step, b_lo += b_step) {
                         if (CY4_DBG != 1 && CY4_DBG != 3 && CY4_DBG != 6) {
-                            umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, kb != 0);
+                            umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, (g0 + j) != 0);
                             umma_f16_lohi(d_tmem, a_lo + 2, dhi, b_lo + 2, dhi, idesc, 1);       // +32 bytes of K per MMA
-                            if (p.kchunk == 64) {
+                            if (k64) {
                                 umma_f16_lohi(d_tmem, a_lo + 4, dhi, b_lo + 4, dhi, idesc, 1);
                                 umma_f16_lohi(d_tmem, a_lo + 6, dhi, b_lo + 6, dhi, idesc, 1);
                             }
@@ -228,8 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (g0 + cnt == num_kb) umma_commit(&ctl->tmem_full[acc]);
                     PROBE_ACC(4);
                 }
-                __syncwarp();
-                PROBE_ACC(5);
+                PROBE_ACC(5);                  // (no __syncwarp: the next elect.sync is the warp's convergence point)
                 PROBE_CNT(6);
                 if (++stage == nst) { stage = 0; phase ^= 1; }
             }

@@ -22,7 +22,6 @@ struct ConvKParams {
     int a_mode;                  // 0: A is a plain [M, K] matrix (tiled TMA) ; 1: im2col TMA
     int cluster;                 // CTAs per cluster sharing (multicasting) the weight slabs: 1, 2 or 4
     int debug;                   // 1: skip MMAs, 2: skip TMA loads (bottleneck experiments)
-    int resident_b;              // >0: number of [block_n x kchunk] weight slabs kept in smem for the whole kernel
     int stages, a_stage, b_stage;   // pipeline depth and per-stage bytes (the 192 KB stage region is split to fit)
     int kps;                     // k-blocks per pipeline slot (one barrier round trip per kps k-blocks)
     int slab_bufs;               // output slabs per epilogue warp (1, 2 or 4): TMA-store latency hiding for narrow layers

@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libcy4.so"))
+# CY4_LIB_NAME selects a side build of the same sources (tools/probe_pipeline.py); the default is the product library
+SO_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", os.environ.get("CY4_LIB_NAME", "libcy4.so")))
 
 c_f = ctypes.c_void_p        # device pointers travel as void*
 c_i64 = ctypes.c_int64

@@ -201,9 +201,10 @@ def test_conv_fp32_output_parity():
         assert (y.cpu() - ref).abs().max().item() <= 1e-3          # measured ~1e-5
 
 
-def test_resident_weight_panel():
-    """Small-K layers keep the whole weight panel in shared memory: same results as the streaming path,
-    checked on shapes with more tiles than SMs (3x3 s1/s2, 1x1, Cin=32, stride-2 dgrad parity classes)."""
+def test_kblocks_per_slot():
+    """Narrow layers pack up to 4 k-blocks into one pipeline slot (one barrier round trip per slot): bit-identical
+    to one k-block per slot (same MMA order), checked on shapes with more tiles than SMs (3x3 s1/s2, 1x1, Cin=32,
+    a k loop that is not a multiple of the packing, stride-2 dgrad parity classes)."""
     from cy4 import _lib, convops as co
     L = _lib.lib()
     torch.manual_seed(31)
@@ -216,10 +217,10 @@ def test_resident_weight_panel():
         dy = torch.randn(B, Ho, Ho, Cout, device="cuda").half()
         wp, wd = co.pack_fprop(w.float()), co.pack_dgrad(w.float())
         outs = []
-        for res in (1, 0):
-            _lib.check(L.cy4_set_option(b"resident_weights", res))
+        for kps in (4, 1):
+            _lib.check(L.cy4_set_option(b"kblocks_per_slot", kps))
             outs.append((co.conv_fwd(x, wp, Cout, k, stride, pad), co.conv_dgrad(dy, wd, H, W, Cin, k, stride, pad)))
-        _lib.check(L.cy4_set_option(b"resident_weights", 0))
+        _lib.check(L.cy4_set_option(b"kblocks_per_slot", 4))
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
         ref = _ref_conv(x, w, stride, pad)
         assert (outs[0][0].float().cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3

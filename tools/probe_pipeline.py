@@ -1,13 +1,14 @@
 """Cycle probes of the conv kernel's TMA-producer and MMA-issuer loops (block 0 only).
-Build first with  CY4_EXTRA_NVCC_FLAGS=-DCY4_PROBE python complex-yolov4-pytorch_b200/csrc/build.py
-(the product build has no probes)."""
+Build first with  CY4_LIB_NAME=libcy4_probe.so CY4_EXTRA_NVCC_FLAGS=-DCY4_PROBE python complex-yolov4-pytorch_b200/csrc/build.py
+(the product build has no probes and ignores the "debug" option)."""
 import ctypes, os, sys
+os.environ["CY4_LIB_NAME"] = "libcy4_probe.so"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "complex-yolov4-pytorch_b200"))
 import torch
 from cy4 import _lib, convops as co
 L = _lib.lib()
-raw = ctypes.CDLL(os.path.join(ROOT, "complex-yolov4-pytorch_b200", "csrc", "libcy4.so"))
+raw = ctypes.CDLL(os.path.join(ROOT, "complex-yolov4-pytorch_b200", "csrc", "libcy4_probe.so"))
 B = 32
 buf = (ctypes.c_ulonglong * 16)()
 names_m = ["wait_tmem_empty", "wait_full", "fence", "mma_issue", "commit", "syncwarp"]
