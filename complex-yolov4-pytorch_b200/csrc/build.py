@@ -24,6 +24,7 @@ COMMON += os.environ.get("CY4_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DCY4_P
 PER_FILE = {
     "rgiou.cu": ["--fmad=false"],
     "yolo_head.cu": ["--fmad=false"],
+    "nms.cu": ["--fmad=false"],
 }
 
 

@@ -41,6 +41,14 @@ _SIGS = {
     "cy4_yolo_loss_fwd": (ctypes.c_int, [ctypes.POINTER(YoloDesc), c_f, c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_vp, c_vp]),
     "cy4_yolo_loss_bwd": (ctypes.c_int, [ctypes.POINTER(YoloDesc), c_f, c_f, c_f, c_i64, c_f, c_vp, c_f,
                                         c_i64, c_i64, c_i64, c_i64, c_vp]),
+    # evaluation
+    "cy4_rbox_iou_matrix": (ctypes.c_int, [c_f, c_i64, c_f, c_i64, c_f, c_vp]),
+    "cy4_nms_max_candidates": (ctypes.c_int, []),
+    "cy4_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "cy4_nms_rotated_v2": (ctypes.c_int, [c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, c_f,
+                                         c_vp, c_vp, c_vp, c_vp]),
+    "cy4_eval_max_annotations": (ctypes.c_int, []),
+    "cy4_eval_match": (ctypes.c_int, [c_f, c_vp, ctypes.c_int, ctypes.c_int, c_f, c_i64, ctypes.c_float, c_vp, c_vp, c_vp]),
     "cy4_build_targets": (ctypes.c_int, [ctypes.POINTER(YoloDesc), c_f, c_f, c_f, c_i64, c_f] + [c_f] * 13 +
                           [c_f, c_f, c_vp, c_vp]),
 }

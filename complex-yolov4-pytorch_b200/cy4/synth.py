@@ -55,3 +55,48 @@ def make_bev(batch, seed=1234, img_size=608, channels=3):
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)
     return torch.rand(batch, channels, img_size, img_size, generator=g, dtype=torch.float32)
+
+
+def make_detections(batch, targets, n_rows=22743, n_classes=3, dup=6, clutter=40, seed=99, img_size=608,
+                    conf_lo=0.5, margin=None):
+    """Raw network output [B, n_rows, 7+nC] fp32 (x, y, w, l, im, re, conf, cls...) in pixels, as Darknet.forward
+    returns it in eval mode (reference darknet2pytorch.py:228), for the post-processing / evaluation path:
+    `dup` jittered high-confidence copies of every target (so NMS has clusters to merge, most of them true
+    positives), `clutter` random confident boxes per image (false positives), the rest background with
+    conf < 0.3.  Scores are distinct.  targets: make_targets() output ([nT,8], x..l normalised).
+    margin=(nms_thresh, iou_thresh, eps): hook for tests that need decisions away from the thresholds (unused
+    by default; tests filter with the oracle instead)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((batch, n_rows, 7 + n_classes), np.float32)
+    out[:, :, 0:2] = rng.uniform(0, img_size, (batch, n_rows, 2))
+    out[:, :, 2] = rng.uniform(8, 30, (batch, n_rows)); out[:, :, 3] = rng.uniform(12, 70, (batch, n_rows))
+    yaw = rng.uniform(-math.pi, math.pi, (batch, n_rows))
+    out[:, :, 4] = np.sin(yaw); out[:, :, 5] = np.cos(yaw)
+    out[:, :, 6] = rng.uniform(0.0, 0.3, (batch, n_rows))
+    out[:, :, 7:] = rng.uniform(0.0, 1.0, (batch, n_rows, n_classes))
+    for b in range(batch):
+        tg = targets[targets[:, 0] == b]
+        rows = rng.choice(n_rows, size=len(tg) * dup + clutter, replace=False)
+        confs = rng.permutation(np.linspace(conf_lo + 0.01, 0.999, len(rows))).astype(np.float32)     # distinct
+        k = 0
+        for t in tg:
+            cls = int(t[1])
+            x, y, w, l = t[2] * img_size, t[3] * img_size, t[4] * img_size, t[5] * img_size
+            tyaw = math.atan2(t[6], t[7])
+            for _ in range(dup):
+                r = rows[k]
+                jy = tyaw + rng.normal(0, 0.06)
+                amp = rng.uniform(0.9, 1.1)                      # im/re are not normalised by the network
+                out[b, r, :6] = [x + rng.normal(0, 1.5), y + rng.normal(0, 1.5), w * math.exp(rng.normal(0, 0.06)),
+                                 l * math.exp(rng.normal(0, 0.06)), amp * math.sin(jy), amp * math.cos(jy)]
+                out[b, r, 6] = confs[k]
+                pc = rng.uniform(0.0, 0.3, n_classes); pc[cls if rng.uniform() < 0.9 else (cls + 1) % n_classes] = rng.uniform(0.7, 1.0)
+                out[b, r, 7:] = pc
+                k += 1
+        for _ in range(clutter):
+            r = rows[k]
+            out[b, r, 6] = confs[k]
+            pc = rng.uniform(0.0, 0.3, n_classes); pc[int(rng.integers(0, n_classes))] = rng.uniform(0.7, 1.0)
+            out[b, r, 7:] = pc
+            k += 1
+    return out

@@ -226,6 +226,32 @@ CY4_API int cy4_make_scale(const float *amax, float target, float *scale2, void 
 /* out[c] (+)= scale * sum_m src[m, c]  (bias gradient of the head convs) */
 CY4_API int cy4_colsum_f32(const float *src, int64_t lds, int64_t M, int C, float scale, float *out, int accumulate, void *stream);
 
+/* ---- evaluation ---------------------------------------------------------
+ * utils/evaluation_utils.py:186-210 iou_rotated_single_vs_multi_boxes_cpu, generalised to all pairs:
+ * ious[i*m + j] = IoU(a6[i], b6[j]); rows (x, y, w, l, im, re).  fp32 corners, fp64 polygon intersection
+ * (shapely in the reference), iou = reciprocal(area_a + area_b - inter + 1e-16) * inter in fp32. */
+CY4_API int cy4_rbox_iou_matrix(const float *a6, int64_t n, const float *b6, int64_t m, float *ious, void *stream);
+
+/* utils/evaluation_utils.py:322-357 post_processing_v2 on the device, one CTA per image.
+ * pred [B, N, 7+nC] (x,y,w,l,im,re,conf,cls...); rows with conf >= conf_thresh, sorted by conf*max(cls)
+ * (ties: lower row first), greedy rotated NMS over same-class boxes with IoU > nms_thresh, kept box =
+ * confidence-weighted mean of the boxes it suppresses.  out9 [B, cy4_nms_max_candidates(), 9] rows
+ * (merged box 6, conf, cls_conf, cls_pred), counts[B] kept rows, found[B] rows that passed the filter
+ * (found > cy4_nms_max_candidates(): the list was truncated -- treat as an error).
+ * workspace: cy4_nms_workspace_bytes(B) bytes. */
+CY4_API int cy4_nms_max_candidates(void);
+CY4_API size_t cy4_nms_workspace_bytes(int B);
+CY4_API int cy4_nms_rotated_v2(const float *pred, int B, int N, int nC, float conf_thresh, float nms_thresh, float *out9,
+                               int32_t *counts, int32_t *found, void *workspace, void *stream);
+
+/* utils/evaluation_utils.py:152-183 get_batch_statistics_rotated_bbox: true-positive flags of the
+ * detections of every image against targets8 [nT,8] rows (img, cls, x, y, w, l, im, re; x..l in pixels).
+ * dets9 [B, max_det, 9] / counts[B] as written by cy4_nms_rotated_v2; tp [B, max_det] (0/1);
+ * n_ann[B] annotations found per image (> cy4_eval_max_annotations(): truncated -- treat as an error). */
+CY4_API int cy4_eval_max_annotations(void);
+CY4_API int cy4_eval_match(const float *dets9, const int32_t *counts, int B, int max_det, const float *targets8, int64_t nT,
+                           float iou_thresh, uint8_t *tp, int32_t *n_ann, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

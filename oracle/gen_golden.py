@@ -221,11 +221,50 @@ def gen_darknet_emu16(cfg, tag, batch, n_targets, k_samples=2048):
          **{f"metrics{i}": np.array([m[k] for k in mk], np.float64) for i, m in enumerate(mets)}, **acts, **grads)
 
 
+def gen_eval(m):
+    """Section 8 row f1: the reference's post_processing_v2, one-vs-many IoU, true-positive matching and AP
+    (utils/evaluation_utils.py) on seeded synthetic detections."""
+    ev = m["eval"]
+    B, N = 4, 3000
+    tg = synth.make_targets(B, per_image=6, seed=77)
+    pred = synth.make_detections(B, tg, n_rows=N, dup=5, clutter=25, seed=99)
+    conf_thresh, nms_thresh, iou_thresh = 0.5, 0.4, 0.5
+    outs = ev.post_processing_v2(torch.tensor(pred), conf_thresh=conf_thresh, nms_thresh=nms_thresh)
+    tgt_px = torch.tensor(tg).clone()
+    tgt_px[:, 2:6] *= 608                                            # evaluate.py:41
+    stats = ev.get_batch_statistics_rotated_bbox(outs, tgt_px, iou_threshold=iou_thresh)
+    res = {"pred": pred, "targets_px": tgt_px.numpy(), "conf_thresh": conf_thresh, "nms_thresh": nms_thresh, "iou_thresh": iou_thresh,
+           "none_mask": np.array([o is None for o in outs])}
+    for i, o in enumerate(outs):
+        if o is not None:
+            res["out_%d" % i] = o.numpy()
+    for i, (tp, sc, lb) in enumerate(stats):
+        res["tp_%d" % i] = np.asarray(tp); res["score_%d" % i] = np.asarray(sc); res["label_%d" % i] = np.asarray(lb)
+    tp = np.concatenate([s_[0] for s_ in stats]); sc = np.concatenate([np.asarray(s_[1]) for s_ in stats])
+    lb = np.concatenate([np.asarray(s_[2]) for s_ in stats])
+    import io, contextlib
+    with contextlib.redirect_stderr(io.StringIO()):
+        p_, r_, ap_, f1_, cls_ = ev.ap_per_class(tp, sc, lb, tg[:, 1].tolist())
+    res.update(ap_precision=p_, ap_recall=r_, ap_AP=ap_, ap_f1=f1_, ap_classes=cls_)
+    # one-vs-many IoU on its own: detections of image 0 against that image's targets and against themselves
+    o0 = outs[0]
+    t0 = tgt_px[tgt_px[:, 0] == 0][:, 2:]
+    res["iou_det_vs_tgt"] = np.stack([ev.iou_rotated_single_vs_multi_boxes_cpu(o0[i, :6], t0).numpy() for i in range(o0.shape[0])])
+    res["iou_det_vs_det"] = np.stack([ev.iou_rotated_single_vs_multi_boxes_cpu(o0[i, :6], o0[:, :6]).numpy() for i in range(min(16, o0.shape[0]))])
+    # an image without any confident row -> None
+    empty = pred[:1].copy(); empty[:, :, 6] *= 0.1
+    res["empty_is_none"] = np.array([ev.post_processing_v2(torch.tensor(empty), conf_thresh, nms_thresh)[0] is None])
+    res["shapely_kind"] = np.array(m["shapely_kind"])
+    save("eval_nms_b4.npz", **res)
+    print("kept per image:", [None if o is None else o.shape[0] for o in outs], " TP:", int(tp.sum()), "of", len(tp), " AP:", ap_)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     m = rl.load()
-    which = sys.argv[1:] or ["pairs", "anchor", "yolo", "tiny", "v4", "emu"]
+    which = sys.argv[1:] or ["pairs", "anchor", "yolo", "tiny", "v4", "emu", "eval"]
+    if "eval" in which: gen_eval(m)
     if "pairs" in which: gen_pairs(m)
     if "anchor" in which: gen_anchor_iou(m)
     if "yolo" in which: gen_yolo_layer(m)

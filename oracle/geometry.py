@@ -39,6 +39,7 @@ def lib():
         L.orc_anchor_iou.argtypes = [fp, ctypes.c_int, fp, ctypes.c_int64, fp]
         L.orc_rgiou_pairs.argtypes = [fp, fp, ctypes.c_int64, ctypes.c_uint32, fp, fp, fp]
         L.orc_rgiou_pairs_exact64.argtypes = [fp, fp, ctypes.c_int64, dp, dp]
+        L.orc_iou_matrix.argtypes = [fp, ctypes.c_int64, fp, ctypes.c_int64, fp]
         _lib = L
     return _lib
 
@@ -100,3 +101,12 @@ def rgiou_pairs_exact64(pred6, tgt6):
     dp = ctypes.POINTER(ctypes.c_double)
     lib().orc_rgiou_pairs_exact64(_p(p), _p(t), n, iou.ctypes.data_as(dp), term.ctypes.data_as(dp))
     return iou, term
+
+
+def iou_matrix(a6, b6):
+    """IoU of every box of a6 [n,6] with every box of b6 [m,6] -> [n,m] fp32 (evaluation_utils.py:186-210)."""
+    a, b = _f32(a6).reshape(-1, 6), _f32(b6).reshape(-1, 6)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    if a.shape[0] and b.shape[0]:
+        lib().orc_iou_matrix(_p(a), a.shape[0], _p(b), b.shape[0], _p(out))
+    return out

@@ -242,6 +242,30 @@ void orc_anchor_iou(const float *anchors4, int nA, const float *tgt4, int64_t nT
     }
 }
 
+/* utils/evaluation_utils.py:186-210  iou_rotated_single_vs_multi_boxes_cpu, for every pair (a[i], b[j]).
+ * rows (x, y, w, l, im, re).  Corners in fp32 (bev_utils.get_corners / get_corners_vectorize :213-239, same
+ * left-to-right order as orc_corners), intersection exact in fp64 (shapely), then fp32:
+ * iou = reciprocal((s_area + m_area) - inter + 1e-16) * inter   (python float / tensor). */
+void orc_iou_matrix(const float *a6, int64_t n, const float *b6, int64_t m, float *ious)
+{
+    int64_t i, j;
+    for (i = 0; i < n; ++i) {
+        const float *A = a6 + 6 * i;
+        float ac[4][2];
+        orc_corners(A[0], A[1], A[2], A[3], atan2f(A[4], A[5]), ac);
+        float aa = A[2] * A[3];
+        for (j = 0; j < m; ++j) {
+            const float *B = b6 + 6 * j;
+            float bc[4][2];
+            orc_corners(B[0], B[1], B[2], B[3], atan2f(B[4], B[5]), bc);
+            float ba = B[2] * B[3];
+            float inter = (float)clip_area64(ac, bc);
+            float den = ((aa + ba) - inter) + 1e-16f;
+            ious[i * m + j] = (1.0f / den) * inter;
+        }
+    }
+}
+
 /* utils/iou_rotated_boxes_utils.py:98-142  iou_pred_vs_target_boxes, element-wise pairs.
  * flags bit0: GIoU (reference clipper :122 + hull term :128-133); otherwise the shapely path
  * (:118-120, exact intersection) with term = 1 - iou (:135).

@@ -22,8 +22,8 @@ def load():
     # The reference imports its own top-level packages `models`, `utils`.  Make sure ours
     # (complex-yolov4-pytorch_b200/) do not shadow them while loading, then restore.
     saved_path = list(sys.path)
-    saved_mods = {k: sys.modules.pop(k) for k in list(sys.modules)
-                  if k in ("models", "utils") or k.startswith("models.") or k.startswith("utils.")}
+    pk = ("models", "utils", "data_process", "config")
+    saved_mods = {k: sys.modules.pop(k) for k in list(sys.modules) if k in pk or k.split(".")[0] in pk}
     sys.path = [REF_SRC] + [p for p in sys.path if "complex-yolov4-pytorch_b200" not in p]
     try:
         mods = {
@@ -31,10 +31,11 @@ def load():
             "iou": importlib.import_module("utils.iou_rotated_boxes_utils"),
             "yolo": importlib.import_module("models.yolo_layer"),
             "darknet": importlib.import_module("models.darknet2pytorch"),
+            "eval": importlib.import_module("utils.evaluation_utils"),        # section 8 row f1
         }
     finally:
         for k in list(sys.modules):
-            if k in ("models", "utils") or k.startswith("models.") or k.startswith("utils."):
+            if k in pk or k.split(".")[0] in pk:
                 sys.modules["_ref_" + k] = sys.modules.pop(k)
         sys.modules.update(saved_mods)
         sys.path = saved_path
