@@ -25,6 +25,12 @@ class YoloDesc(ctypes.Structure):
                 ("use_giou", c_u32), ("reserved", c_u32)]
 
 
+class BevDesc(ctypes.Structure):
+    _fields_ = [("minX", ctypes.c_float), ("maxX", ctypes.c_float), ("minY", ctypes.c_float), ("maxY", ctypes.c_float),
+                ("minZ", ctypes.c_float), ("maxZ", ctypes.c_float), ("discretization", ctypes.c_float), ("max_height", ctypes.c_float),
+                ("H", c_i32), ("W", c_i32), ("apply_filter", c_i32), ("reserved", c_i32)]
+
+
 _SIGS = {
     "cy4_version": (ctypes.c_int, []),
     "cy4_last_error": (ctypes.c_char_p, []),
@@ -49,6 +55,9 @@ _SIGS = {
                                          c_vp, c_vp, c_vp, c_vp]),
     "cy4_eval_max_annotations": (ctypes.c_int, []),
     "cy4_eval_match": (ctypes.c_int, [c_f, c_vp, ctypes.c_int, ctypes.c_int, c_f, c_i64, ctypes.c_float, c_vp, c_vp, c_vp]),
+    # LiDAR -> BEV rasteriser
+    "cy4_bev_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "cy4_bev_rasterize": (ctypes.c_int, [c_f, c_vp, ctypes.c_int, ctypes.POINTER(BevDesc), c_f, c_vp, c_vp, c_vp]),
     "cy4_build_targets": (ctypes.c_int, [ctypes.POINTER(YoloDesc), c_f, c_f, c_f, c_i64, c_f] + [c_f] * 13 +
                           [c_f, c_f, c_vp, c_vp]),
 }

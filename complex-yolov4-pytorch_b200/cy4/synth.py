@@ -100,3 +100,28 @@ def make_detections(batch, targets, n_rows=22743, n_classes=3, dup=6, clutter=40
             out[b, r, 7:] = pc
             k += 1
     return out
+
+
+def make_point_cloud(n=120000, seed=5, ties=True):
+    """[n,4] fp32 (x, y, z, intensity) LiDAR-like frame for the BEV rasteriser: ~60 % of the points inside the front
+    KITTI boundary (0..50 m, -25..25 m, -2.73..1.27 m) with a 1/r density, ground plane + object clusters, the rest
+    outside (to exercise removePoints); `ties` adds exact duplicates of heights within a cell and points exactly on
+    the inclusive bounds."""
+    rng = np.random.default_rng(seed)
+    r = 3.0 + 70.0 * rng.uniform(0, 1, n) ** 2
+    th = rng.uniform(-math.pi, math.pi, n)
+    x, y = r * np.cos(th), r * np.sin(th)
+    z = -1.7 + 0.05 * rng.normal(size=n)
+    obj = rng.uniform(size=n) < 0.25
+    z[obj] = rng.uniform(-1.7, 1.5, obj.sum())
+    out_z = rng.uniform(size=n) < 0.02
+    z[out_z] = rng.uniform(-4.0, 3.0, out_z.sum())
+    pts = np.stack([x, y, z, rng.uniform(0, 1, n)], 1).astype(np.float32)
+    if ties:
+        k = min(2000, n // 10)
+        src = rng.choice(n, k, replace=False); dst = rng.choice(n, k, replace=False)
+        pts[dst, :3] = pts[src, :3]                                  # same cell, same height, different intensity
+        edge = rng.choice(n, 64, replace=False)
+        pts[edge[:16], 0] = 0.0; pts[edge[16:32], 0] = 50.0; pts[edge[32:40], 1] = -25.0; pts[edge[40:48], 1] = 25.0
+        pts[edge[48:56], 2] = np.float32(-2.73); pts[edge[56:], 2] = np.float32(1.27)
+    return pts

@@ -252,6 +252,26 @@ CY4_API int cy4_eval_max_annotations(void);
 CY4_API int cy4_eval_match(const float *dets9, const int32_t *counts, int B, int max_det, const float *targets8, int64_t nT,
                            float iou_thresh, uint8_t *tp, int32_t *n_ann, void *stream);
 
+/* ---- LiDAR -> BEV rasteriser ---------------------------------------------
+ * data_process/kitti_bev_utils.py:18-36 removePoints + :39-76 makeBVFeature for a batch of frames.
+ * points4: all frames' (x, y, z, intensity) fp32 rows back to back (16-byte aligned), offsets[B+1] row
+ * offsets of the frames.  out [B, 3, H, W] fp32: channel 0 intensity of the highest point of the cell
+ * (first in file order among equal heights), 1 its height / max_height, 2 min(1, log(count+1)/log(64)).
+ * apply_filter = 1: removePoints first (inclusive bounds, z -= minZ); 0: points are already filtered / shifted
+ * (the reference's makeBVFeature contract).  dropped[B]: points that fall outside even the reference's
+ * (H+1) x (W+1) scratch map (numpy would wrap or raise there).  workspace: cy4_bev_workspace_bytes(). */
+typedef struct cy4_bev_desc {
+    float minX, maxX, minY, maxY, minZ, maxZ;
+    float discretization;   /* metres per cell: (maxX - minX) / H, config/kitti_config.py:36 */
+    float max_height;       /* float(abs(maxZ - minZ)), kitti_bev_utils.py:58 */
+    int32_t H, W;           /* 608 x 608 */
+    int32_t apply_filter;
+    int32_t reserved;
+} cy4_bev_desc;
+CY4_API size_t cy4_bev_workspace_bytes(int B, int H, int W);
+CY4_API int cy4_bev_rasterize(const float *points4, const int64_t *offsets, int B, const cy4_bev_desc *desc, float *out,
+                              int32_t *dropped, void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -259,12 +259,32 @@ def gen_eval(m):
     print("kept per image:", [None if o is None else o.shape[0] for o in outs], " TP:", int(tp.sum()), "of", len(tp), " AP:", ap_)
 
 
+def gen_bev(m):
+    """Section 8 row f3: the reference's removePoints + makeBVFeature + build_yolo_target
+    (data_process/kitti_bev_utils.py) on a seeded synthetic LiDAR frame."""
+    kb = sys.modules["_ref_data_process.kitti_bev_utils"]
+    cnf = sys.modules["_ref_config.kitti_config"]
+    pts = synth.make_point_cloud(30000, seed=5)
+    b = kb.removePoints(pts.copy(), cnf.boundary)
+    rgb = kb.makeBVFeature(b, cnf.DISCRETIZATION, cnf.boundary)            # float64 [3,608,608]
+    nz = np.flatnonzero((rgb != 0).any(axis=0))
+    rng = np.random.default_rng(8)
+    labels = np.stack([rng.integers(0, 3, 40).astype(np.float64), rng.uniform(-5, 60, 40), rng.uniform(-30, 30, 40), rng.uniform(-2, 0, 40),
+                       rng.uniform(1.4, 1.9, 40), rng.uniform(0.5, 2.0, 40), rng.uniform(0.8, 4.5, 40), rng.uniform(-np.pi, np.pi, 40)], 1)
+    tgt = kb.build_yolo_target(labels.astype(np.float32))
+    save("bev_raster.npz", points=pts, filtered_rows=np.int64(b.shape[0]), filtered_head=b[:64], nz_cells=nz.astype(np.int32),
+         nz_values=rgb.reshape(3, -1)[:, nz], labels=labels.astype(np.float32), yolo_target=tgt,
+         discretization=np.float64(cnf.DISCRETIZATION))
+    print("points", pts.shape, "inside", b.shape[0], "occupied cells", len(nz), "targets", tgt.shape)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     m = rl.load()
-    which = sys.argv[1:] or ["pairs", "anchor", "yolo", "tiny", "v4", "emu", "eval"]
+    which = sys.argv[1:] or ["pairs", "anchor", "yolo", "tiny", "v4", "emu", "eval", "bev"]
     if "eval" in which: gen_eval(m)
+    if "bev" in which: gen_bev(m)
     if "pairs" in which: gen_pairs(m)
     if "anchor" in which: gen_anchor_iou(m)
     if "yolo" in which: gen_yolo_layer(m)

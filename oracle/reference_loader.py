@@ -31,7 +31,7 @@ def load():
             "iou": importlib.import_module("utils.iou_rotated_boxes_utils"),
             "yolo": importlib.import_module("models.yolo_layer"),
             "darknet": importlib.import_module("models.darknet2pytorch"),
-            "eval": importlib.import_module("utils.evaluation_utils"),        # section 8 row f1
+            "eval": importlib.import_module("utils.evaluation_utils"),        # section 8 row f1 (pulls in data_process.kitti_bev_utils, row f3)
         }
     finally:
         for k in list(sys.modules):
