@@ -237,6 +237,42 @@ def run_ours(args):
                 giou["reference_python_pairs_per_s"] = "1152 (survey container, BASELINE.md section 4; the Python reference cannot run on the GPU box)"
             giou[str(n)] = {"us": round(t * 1e3, 2), "pairs_per_s": round(n / (t / 1e3), 0), "GBps": round(n * 56 / (t / 1e3) / 1e9, 1),
                             "hbm_frac": round(n * 56 / (t / 1e3) / 1e9 / pk["hbm_gbs"], 4)}
+        # ---- the "next" rows built so far, outside the timed region; a failure here must
+        # not cost the headline line, so each is guarded and reports its error instead
+        nxt = {}
+        try:
+            from cy4 import evalops
+            tgs = synth.make_targets(B, per_image=8, seed=11)
+            dets_h = synth.make_detections(B, tgs, n_rows=22743, dup=8, clutter=150, seed=3)
+            pd_ = torch.tensor(dets_h, device=dev)
+            tpx = tgs.copy(); tpx[:, 2:6] *= 608
+            td2 = torch.tensor(tpx, device=dev)
+            for _ in range(2):
+                dd = evalops.nms_v2(pd_, 0.5, 0.4); evalops.match(dd, td2, 0.5)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(5):
+                dd = evalops.nms_v2(pd_, 0.5, 0.4); evalops.match(dd, td2, 0.5)
+            b.record(); torch.cuda.synchronize()
+            nxt["f1_rotated_nms_and_matching"] = {"ms_per_batch": round(a.elapsed_time(b) / 5, 3), "batch": B, "rows_per_image": 22743,
+                                                  "candidates_per_image": int((dets_h[0, :, 6] >= 0.5).sum())}
+        except Exception as e:      # noqa: BLE001
+            nxt["f1_rotated_nms_and_matching"] = {"error": repr(e)[:300]}
+        try:
+            from cy4 import bevops
+            clouds = [torch.tensor(synth.make_point_cloud(120000, seed=100 + i, ties=False), device=dev) for i in range(B)]
+            for _ in range(2):
+                bevops.rasterize(clouds)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(5):
+                bevops.rasterize(clouds)
+            b.record(); torch.cuda.synchronize()
+            t_ = a.elapsed_time(b) / 5
+            nxt["f3_lidar_to_bev"] = {"ms_per_batch": round(t_, 3), "batch": B, "points_per_frame": 120000,
+                                      "algorithmic_GBps": round(B * (120000 * 16 + 3 * 608 * 608 * 4) / (t_ / 1e3) / 1e9, 1)}
+        except Exception as e:      # noqa: BLE001
+            nxt["f3_lidar_to_bev"] = {"error": repr(e)[:300]}
         result = {
             "metric": "BEV-images/sec training step (bs=32, 608x608)", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
@@ -253,6 +289,7 @@ def run_ours(args):
             "fwd_tensor_frac_of_step_flops": None,
             "step_tflops": round(3 * GFLOP_FWD_PER_IMG.get(args.cfg, 0) * B * 1e-3 / (ms_per_step / 1e3), 1),
             "rgiou_microbench": giou,
+            "next_rows": nxt,
         }
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_step_baseline(args.cfg, budget_s=25.0)
