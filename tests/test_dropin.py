@@ -96,3 +96,34 @@ def test_netdefs_match_reference_cfgs():
                 if k == "batch_normalize":
                     va, vb = int(va), int(vb)
                 assert va == vb, (name, k, va, vb)
+
+
+def test_next_row_modules_expose_reference_names():
+    """Rows f1 / f3: the names evaluate.py, test.py and kitti_dataset.py import from the replaced modules exist."""
+    ev = importlib.import_module("utils.evaluation_utils")
+    for name in ("post_processing", "post_processing_v2", "get_batch_statistics_rotated_bbox", "ap_per_class", "load_classes",
+                 "rescale_boxes", "iou_rotated_single_vs_multi_boxes_cpu", "get_corners_vectorize", "compute_ap"):
+        assert callable(getattr(ev, name)), name
+    kb = importlib.import_module("data_process.kitti_bev_utils")
+    for name in ("removePoints", "makeBVFeature", "build_yolo_target"):
+        assert callable(getattr(kb, name)), name
+
+
+def test_bev_dropin_reexports_reference_helpers():
+    """With the reference tree on sys.path (the integration layout of INTEGRATION.md) the rest of kitti_bev_utils -- label
+    reading, corner / drawing helpers -- comes from the reference's own file, and our three functions stay ours."""
+    import os
+    import subprocess
+    import pytest
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not present")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.append('/root/reference/src')\n"
+            "import data_process.kitti_bev_utils as kb\n"
+            "assert kb.makeBVFeature.__module__ == 'data_process.kitti_bev_utils', kb.makeBVFeature.__module__\n"
+            "assert kb.build_yolo_target.__module__ == 'data_process.kitti_bev_utils'\n"
+            "for n in ('read_labels_for_bevbox', 'get_corners', 'inverse_yolo_target', 'drawRotatedBox'):\n"
+            "    assert callable(getattr(kb, n)), n\n"
+            "import data_process.transformation\n"          # falls through to the reference's package directory
+            "print('ok')\n" % PKG)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-800:]
