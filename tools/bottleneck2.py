@@ -1,4 +1,9 @@
 import os, sys
+# The "debug" switches only exist in the probe side build:
+#   CY4_LIB_NAME=libcy4_probe.so CY4_EXTRA_NVCC_FLAGS=-DCY4_PROBE python complex-yolov4-pytorch_b200/csrc/build.py
+# With the product library every column of the table is the full kernel.
+if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "complex-yolov4-pytorch_b200", "csrc", "libcy4_probe.so")):
+    os.environ.setdefault("CY4_LIB_NAME", "libcy4_probe.so")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "complex-yolov4-pytorch_b200"))
 import torch
