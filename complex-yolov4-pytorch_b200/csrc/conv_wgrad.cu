@@ -230,7 +230,21 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     p.debug = g_debug;
     p.cluster = (g_wgrad_cluster >= 2 && !(d->flags & CY4_CONV_A_MATRIX) && p.m_tiles % 2 == 0) ? 2 : 1;
     const int items = p.m_tiles * p.n_tiles * p.tap_groups;
-    p.ksplit = std::max(1, std::min(p.kblocks, (2 * sm_count() + items - 1) / items));
+    // Split-K factor.  One CTA per SM fits (193 KB of smem), so the kernel runs in waves of sm_count() CTAs and a grid of
+    // 300 CTAs costs three CTA durations, not 2.03: pick the split (up to ~2 waves of CTAs) that minimises
+    // waves x (k-blocks per CTA + the fixed prologue / TMEM drain / red.add epilogue, ~6 k-blocks' worth of time).
+    {
+        const int sms = sm_count();
+        const int ks_max = std::max(1, std::min(p.kblocks, (2 * sms + items - 1) / items));
+        double best = 1e30;
+        p.ksplit = 1;
+        for (int ks = 1; ks <= ks_max; ++ks) {
+            const int waves = (items * ks + sms - 1) / sms;
+            const int kb_per = (p.kblocks + ks - 1) / ks;
+            const double cost = (double)waves * (kb_per + 6.0);
+            if (cost < best - 1e-9) { best = cost; p.ksplit = ks; }
+        }
+    }
     p.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
     if (p.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_wgrad: matrix mode needs a 1x1/s1/p0 conv");
     p.Po = d->Ho; p.Qo = d->Wo; p.tstride = d->stride; p.lower_w = p.lower_h = -d->pad;
