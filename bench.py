@@ -278,8 +278,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate, fp32 master weights / loss head)",
             "data": "synthetic",
-            "config": {"workload": "%s.cfg training step (fwd + rotated-GIoU loss + bwd + Adam), bs=%d/GPU, 608x608x3 synthetic BEV, "
-                                   "5 targets/img, GIoU on" % (args.cfg, B),
+            "config": {"workload": workload_name(args.cfg, B),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "no flush needed: per-step working set (>20 GB) exceeds the 126 MB L2"},
             "e2e": {"value": round(world * B * args.steps / float(e2e_s.item()), 2), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
@@ -318,6 +317,12 @@ def usable_cores():
         except Exception:
             pass
     return max(1, min(n, 64))          # beyond ~64 threads the oneDNN convs of this size stop scaling
+
+
+def workload_name(cfg, batch):
+    """config.workload, shared by both arms (the reference arm times a bounded sample of the same workload)."""
+    return ("%s.cfg training step (fwd + rotated-GIoU loss + bwd + Adam), bs=%d/GPU, 608x608x3 synthetic BEV, "
+            "5 targets/img, GIoU on" % (cfg, batch))
 
 
 def cpu_step_baseline(cfg, budget_s=25.0, batch=2):
@@ -363,7 +368,8 @@ def run_reference(args):
     return {"impl": "reference", "metric": "BEV-images/sec training step (bs=32, 608x608)", "value": base["value"], "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(2e3 / base["value"], 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "%s.cfg training step on the host CPU, bounded sample bs=2 per step" % args.cfg},
+            "config": {"workload": workload_name(args.cfg, args.batch), "global_batch": args.batch * world, "parallelism": "host cpu",
+                       "sample": "the same step on the host cores, bounded to bs=2 per step (see cpu_baseline.sample)"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
