@@ -200,18 +200,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 
 using namespace cy4;
 
-extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void *dy, float *dw_acc, void *stream)
+// Tile geometry and split-K factor of one weight-gradient launch (shared by cy4_conv_wgrad and cy4_conv_wgrad_plan).
+static void wgrad_tiling(const cy4_conv_desc *d, WgradParams &p)
 {
-    CY4_CHECK_ARG(d && x && dy && dw_acc, "cy4_conv_wgrad: null pointer");
-    CY4_CHECK_ARG(d->ksize >= 1 && d->ksize <= 3 && d->stride >= 1 && d->stride <= 2, "cy4_conv_wgrad: bad geometry");
     const int k = d->ksize;
-    const int cout64 = (d->Cout + 63) / 64 * 64;
-    CY4_CHECK_ARG(d->ldy >= cout64 && d->ldy % 8 == 0, "cy4_conv_wgrad: dy must be allocated with ld >= Cout rounded up to 64");
-    const bool sw64 = d->Cin == 32;     // one [64 px x 32 ch] box, 64B swizzle: never reads past the 32 channels
+    const bool sw64 = d->Cin == 32;
     const int cin64 = sw64 ? 32 : (d->Cin + 63) / 64 * 64;
-    CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx >= (sw64 ? 32 : cin64) && d->ldx % 8 == 0, "cy4_conv_wgrad: x must be allocated with ld >= Cin rounded up to 64 (or Cin == 32)");
-    WgradParams p;
-    memset(&p, 0, sizeof(p));
     p.Mpix = d->B * d->Ho * d->Wo;
     p.Cout = d->Cout; p.Cin = d->Cin;
     p.m_tiles = (d->Cout + 127) / 128;
@@ -245,6 +239,22 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
             if (cost < best - 1e-9) { best = cost; p.ksplit = ks; }
         }
     }
+}
+
+extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void *dy, float *dw_acc, void *stream)
+{
+    CY4_CHECK_ARG(d && x && dy && dw_acc, "cy4_conv_wgrad: null pointer");
+    CY4_CHECK_ARG(d->ksize >= 1 && d->ksize <= 3 && d->stride >= 1 && d->stride <= 2, "cy4_conv_wgrad: bad geometry");
+    const int k = d->ksize;
+    const int cout64 = (d->Cout + 63) / 64 * 64;
+    CY4_CHECK_ARG(d->ldy >= cout64 && d->ldy % 8 == 0, "cy4_conv_wgrad: dy must be allocated with ld >= Cout rounded up to 64");
+    const bool sw64 = d->Cin == 32;     // one [64 px x 32 ch] box, 64B swizzle: never reads past the 32 channels
+    const int cin64 = sw64 ? 32 : (d->Cin + 63) / 64 * 64;
+    CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx >= (sw64 ? 32 : cin64) && d->ldx % 8 == 0, "cy4_conv_wgrad: x must be allocated with ld >= Cin rounded up to 64 (or Cin == 32)");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    wgrad_tiling(d, p);
+    const int items = p.m_tiles * p.n_tiles * p.tap_groups;
     p.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
     if (p.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_wgrad: matrix mode needs a 1x1/s1/p0 conv");
     p.Po = d->Ho; p.Qo = d->Wo; p.tstride = d->stride; p.lower_w = p.lower_h = -d->pad;
@@ -284,4 +294,16 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     cfg.numAttrs = p.cluster > 1 ? 1 : 0;
     CY4_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tmDy, tmX, p));
     return cy4_launch_status("cy4_conv_wgrad");
+}
+
+extern "C" int cy4_conv_wgrad_plan(const cy4_conv_desc *d, int32_t *out8)
+{
+    CY4_CHECK_ARG(d && out8, "cy4_conv_wgrad_plan: null pointer");
+    CY4_CHECK_ARG(d->ksize >= 1 && d->ksize <= 3 && d->Cin % 32 == 0 && d->Cout > 0 && d->B > 0, "cy4_conv_wgrad_plan: bad geometry");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    wgrad_tiling(d, p);
+    out8[0] = p.m_tiles; out8[1] = p.n_tiles; out8[2] = p.block_n; out8[3] = p.tpc; out8[4] = p.tap_groups;
+    out8[5] = p.kblocks; out8[6] = p.ksplit; out8[7] = p.m_tiles * p.n_tiles * p.tap_groups * p.ksplit;
+    return 0;
 }

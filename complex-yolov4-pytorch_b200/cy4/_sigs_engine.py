@@ -33,6 +33,7 @@ SIGS = {
     "cy4_conv_fwd": (c_i, [PD, c_f, c_f, c_f, c_f, c_f, c_f, c_vp]),
     "cy4_conv_dgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
     "cy4_conv_wgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
+    "cy4_conv_wgrad_plan": (c_i, [PD, c_vp]),
     "cy4_pack_weight_fprop": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_vp]),
     "cy4_pack_weight_dgrad": (c_i, [c_f, c_i, c_i, c_i, c_f, c_vp]),
     "cy4_unpack_wgrad": (c_i, [c_f, c_i, c_i, c_i, c_i, ctypes.c_float, c_f, c_i, c_f, c_vp]),

@@ -158,6 +158,10 @@ CY4_API int cy4_conv_dgrad(const cy4_conv_desc *d, const void *dy, const void *w
 /* dw_acc[Cout_pad][kh*kw][Cin] (fp32, caller-zeroed) += dy^T * im2col(x): split-K partial sums are
  * added with atomics.  cy4_unpack_wgrad then writes the OIHW fp32 gradient of the parameter. */
 CY4_API int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void *dy, float *dw_acc, void *stream);
+/* Host-side tiling of that launch, without launching (tests / tooling): out8 = m_tiles, n_tiles, block_n, taps per CTA,
+ * tap groups, 128-pixel k-blocks, split-K factor, grid size.  One 193 KB CTA fits per SM, so the grid runs in waves of
+ * <SM count> CTAs; the split minimises waves x (k-blocks per CTA + fixed cost). */
+CY4_API int cy4_conv_wgrad_plan(const cy4_conv_desc *d, int32_t *out8);
 
 CY4_API int cy4_pack_weight_fprop(const float *w_oihw, int Cout, int Cin, int ksize, int cin_pad, void *w_packed, void *stream);
 CY4_API int cy4_pack_weight_dgrad(const float *w_oihw, int Cout, int Cin, int ksize, void *w_packed, void *stream);
