@@ -202,6 +202,17 @@ def run_ours(args):
             t = a.elapsed_time(b)
             k = agg.setdefault(name, [0.0, 0.0, 0])
             k[0] += t; k[1] += fl; k[2] += 1
+        # per layer shape (Cin, Cout, k, stride, Ho): where the tensor-core time goes, for the next optimisation round
+        try:
+            by_shape = {}
+            for name, a, b, fl, shape in prof:
+                k2 = by_shape.setdefault((name, tuple(shape)), [0.0, 0.0, 0])
+                k2[0] += a.elapsed_time(b); k2[1] += fl; k2[2] += 1
+            top_shapes = [{"kernel": n_, "cin_cout_k_s_ho": list(sh), "launches_per_step": v[2] // 2, "ms_per_step": round(v[0] / 2, 3),
+                           "tflops": round(v[1] / (v[0] * 1e9), 1) if v[0] else 0.0}
+                          for (n_, sh), v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:24]]
+        except Exception as e:      # noqa: BLE001 -- diagnostics must never cost the headline line
+            top_shapes = [{"error": repr(e)[:200]}]
         conv_ms = sum(v[0] for v in agg.values()) / 2
         tc = {n: {"ms_per_step": v[0] / 2, "tflops": v[1] / (v[0] * 1e9) if v[0] else 0.0, "launches_per_step": v[2] // 2} for n, v in agg.items()}
         fwd = agg.get("cy4_conv_fwd", [1e-9, 0, 1])
@@ -214,7 +225,7 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic,
                 "peak_source": pk["src"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
                 "flops_per_step": fwd[1] / 2, "avg_launch_ms": fwd[0] / max(fwd[2], 1), "by_kernel": tc,
-                "conv_share_of_step": round(conv_ms / ms_per_step, 3)}
+                "top_layer_shapes": top_shapes, "conv_share_of_step": round(conv_ms / ms_per_step, 3)}
         # ---- rotated-GIoU microbench (BASELINE config 4): 100k pairs (latency) and 10^7 pairs (bandwidth)
         from cy4 import geometry as cg
         giou = {}
