@@ -256,6 +256,20 @@ def gen_eval(m):
     res["empty_is_none"] = np.array([ev.post_processing_v2(torch.tensor(empty), conf_thresh, nms_thresh)[0] is None])
     res["shapely_kind"] = np.array(m["shapely_kind"])
     save("eval_nms_b4.npz", **res)
+    # second case at post_processing_v2's default thresholds (0.95 / 0.4): fewer, more confident candidates
+    tg2 = synth.make_targets(3, per_image=9, seed=5)
+    pred2 = synth.make_detections(3, tg2, n_rows=1500, dup=7, clutter=30, seed=17, conf_lo=0.9)
+    outs2 = ev.post_processing_v2(torch.tensor(pred2))
+    t2 = torch.tensor(tg2).clone(); t2[:, 2:6] *= 608
+    stats2 = ev.get_batch_statistics_rotated_bbox(outs2, t2, iou_threshold=0.5)
+    res2 = {"pred": pred2, "targets_px": t2.numpy(), "none_mask": np.array([o is None for o in outs2])}
+    for i, o in enumerate(outs2):
+        if o is not None:
+            res2["out_%d" % i] = o.numpy()
+    for i, (tp_, sc_, lb_) in enumerate(stats2):
+        res2["tp_%d" % i] = np.asarray(tp_); res2["score_%d" % i] = np.asarray(sc_); res2["label_%d" % i] = np.asarray(lb_)
+    save("eval_nms_b3_default_thresh.npz", **res2)
+    print("default thresholds: kept", [None if o is None else o.shape[0] for o in outs2], "TP", [int(s_[0].sum()) for s_ in stats2])
     print("kept per image:", [None if o is None else o.shape[0] for o in outs], " TP:", int(tp.sum()), "of", len(tp), " AP:", ap_)
 
 

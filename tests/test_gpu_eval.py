@@ -54,6 +54,16 @@ def test_post_processing_v2_vs_reference(golden):
     assert ev.post_processing_v2(torch.tensor(empty), 0.5, 0.4) == [None]
 
 
+def test_default_thresholds_vs_reference(golden):
+    import utils.evaluation_utils as ev
+    g = golden("eval_nms_b3_default_thresh.npz")
+    outs = ev.post_processing_v2(torch.tensor(g["pred"]))                     # conf_thresh=0.95, nms_thresh=0.4
+    _check_against(outs, [g["out_%d" % i] for i in range(3)])
+    st = ev.get_batch_statistics_rotated_bbox(outs, torch.tensor(g["targets_px"]), iou_threshold=0.5)
+    for i, (tp, sc, lb) in enumerate(st):
+        assert np.array_equal(tp, g["tp_%d" % i]) and np.array_equal(np.asarray(sc), g["score_%d" % i])
+
+
 def test_batch_statistics_vs_reference(golden):
     import utils.evaluation_utils as ev
     g = golden("eval_nms_b4.npz")
