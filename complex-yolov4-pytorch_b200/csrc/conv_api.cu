@@ -23,6 +23,7 @@ int g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;
 int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 1;
 int g_debug = 0;
 int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disables the packing)
+int g_wgrad_variant = 1;    // 2: experimental persistent kernel (conv_wgrad2.cu), not yet measured
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
@@ -249,6 +250,7 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
     if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
     if (!strcmp(name, "kblocks_per_slot")) { g_kps_max = value < 1 ? 1 : (value > 8 ? 8 : value); return 0; }
+    if (!strcmp(name, "wgrad_variant")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_variant must be 1 or 2"); g_wgrad_variant = value; return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage
     set_error("cy4_set_option: unknown option %s", name);
     return -1;

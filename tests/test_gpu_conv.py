@@ -163,6 +163,30 @@ def test_conv_wgrad(B, H, W, Cin, Cout, k, stride):
     assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("CY4_EXPERIMENTAL"),
+                    reason="experimental persistent wgrad kernel (conv_wgrad2.cu): written after the round's GPU budget was spent; "
+                           "set CY4_EXPERIMENTAL=1 to validate it")
+def test_conv_wgrad_persistent_variant():
+    """cy4_set_option("wgrad_variant", 2): same results as the default kernel up to the fp32 summation order, on the
+    parity cases plus a many-items-per-CTA shape."""
+    from cy4 import _lib, convops as co
+    L = _lib.lib()
+    for (B, H, W, Cin, Cout, k, stride) in WGRAD_CASES + [(8, 76, 76, 128, 128, 3, 1), (8, 152, 152, 32, 64, 3, 2)]:
+        torch.manual_seed(B + H + Cin)
+        pad = (k - 1) // 2
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        x = torch.randn(B, H, W, Cin, device="cuda").half()
+        dy = (torch.randn(B, Ho, Wo, Cout, device="cuda") / (B * Ho * Wo) ** 0.5).half()
+        outs = []
+        for variant in (1, 2):
+            _lib.check(L.cy4_set_option(b"wgrad_variant", variant))
+            try:
+                outs.append(co.unpack_wgrad(co.conv_wgrad(x, dy, Cin, Cout, k, stride, pad), Cout, Cin, k))
+            finally:
+                _lib.check(L.cy4_set_option(b"wgrad_variant", 1))
+        assert (outs[0] - outs[1]).abs().max().item() <= 1e-3 * outs[0].abs().max().item() + 1e-5
+
+
 def test_conv_wgrad_stem_and_narrow():
     """Stem cols matrix (32 wide, 64B-swizzle B operand) and 32-channel tensors stored with ld=64."""
     from cy4 import convops as co
