@@ -43,3 +43,12 @@ for k, v in base.items():
     L.cy4_set_option(k, v)
 net.use_cuda_graph = True
 print("%-34s %.3f ms/step" % ("defaults + CUDA graph", timed(warm=5)), flush=True)
+# experimental kernels last (a failure here must not hide the numbers above)
+net.use_cuda_graph = False
+try:
+    L.cy4_set_option(b"wgrad_variant", 2)
+    print("%-34s %.3f ms/step" % ("wgrad_variant=2 (persistent, experimental)", timed()), flush=True)
+except Exception as e:      # noqa: BLE001
+    print("wgrad_variant=2 failed:", repr(e)[:300], flush=True)
+finally:
+    L.cy4_set_option(b"wgrad_variant", 1)
