@@ -43,5 +43,8 @@ int make_tmap_im2col(CUtensorMap *tm, const void *base, int C, int W, int H, int
                      int upper_w, int upper_h, int chan_per_pixel, int pixels_per_col, int tstride, int swizzle_bytes,
                      int dtype_bf16);
 int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const ConvKParams &p, cudaStream_t st);
+// experimental CTA-pair (cta_group::2) variant, conv_pair.cu; tmB must be encoded with a box of block_n / 2 rows
+bool conv_pair_eligible(const ConvKParams &p);
+int launch_conv_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const ConvKParams &p, cudaStream_t st);
 
 }  // namespace cy4

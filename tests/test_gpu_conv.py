@@ -187,6 +187,40 @@ def test_conv_wgrad_persistent_variant():
         assert (outs[0] - outs[1]).abs().max().item() <= 1e-3 * outs[0].abs().max().item() + 1e-5
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("CY4_EXPERIMENTAL"),
+                    reason="experimental CTA-pair conv kernel (conv_pair.cu): written after the round's GPU budget was spent; "
+                           "set CY4_EXPERIMENTAL=1 to validate it")
+def test_conv_pair_variant():
+    """cy4_set_option("conv_pair", 1): the cta_group::2 kernel against the default one (same K order: expect identical
+    fp16 outputs) and the fp32 reference, for fprop (+BN statistics), stride-1 / stride-2 dgrad, odd m-tile counts."""
+    from cy4 import _lib, convops as co
+    L = _lib.lib()
+    torch.manual_seed(77)
+    for (B, H, W, Cin, Cout, k, stride) in [(2, 38, 38, 256, 512, 3, 1), (3, 19, 19, 512, 256, 1, 1), (2, 76, 76, 128, 128, 3, 1),
+                                            (1, 38, 38, 256, 256, 3, 1), (2, 76, 76, 128, 256, 3, 2), (16, 38, 38, 256, 512, 3, 1)]:
+        pad = (k - 1) // 2
+        x = torch.randn(B, H, W, Cin, device="cuda").half()
+        w = (torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).half()
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        dy = torch.randn(B, Ho, Wo, Cout, device="cuda").half()
+        wp, wd = co.pack_fprop(w.float()), co.pack_dgrad(w.float())
+        res = []
+        for pair in (0, 1):
+            _lib.check(L.cy4_set_option(b"conv_pair", pair))
+            try:
+                s1 = torch.zeros(Cout, device="cuda"); s2 = torch.zeros(Cout, device="cuda")
+                y = co.conv_fwd(x, wp, Cout, k, stride, pad, stats=(s1, s2))
+                dx = co.conv_dgrad(dy, wd, H, W, Cin, k, stride, pad)
+                torch.cuda.synchronize()
+                res.append((y.clone(), dx.clone(), s1.clone(), s2.clone()))
+            finally:
+                _lib.check(L.cy4_set_option(b"conv_pair", 0))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        assert (res[0][2] - res[1][2]).abs().max().item() <= 1e-3 * res[0][2].abs().max().item() + 1e-3
+        ref = _ref_conv(x, w, stride, pad)
+        assert (res[1][0][..., :Cout].float().cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
 def test_conv_wgrad_stem_and_narrow():
     """Stem cols matrix (32 wide, 64B-swizzle B operand) and 32-channel tensors stored with ld=64."""
     from cy4 import convops as co

@@ -52,3 +52,10 @@ except Exception as e:      # noqa: BLE001
     print("wgrad_variant=2 failed:", repr(e)[:300], flush=True)
 finally:
     L.cy4_set_option(b"wgrad_variant", 1)
+try:
+    L.cy4_set_option(b"conv_pair", 1)
+    print("%-34s %.3f ms/step" % ("conv_pair=1 (cta_group::2, experimental)", timed()), flush=True)
+except Exception as e:      # noqa: BLE001
+    print("conv_pair=1 failed:", repr(e)[:300], flush=True)
+finally:
+    L.cy4_set_option(b"conv_pair", 0)
