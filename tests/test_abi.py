@@ -49,3 +49,18 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "rbox_oracle" in src:
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_set_option_names_and_ranges():
+    """cy4_set_option is host-only state: every documented tunable parses, bad names / values are rejected with an
+    error string, and the defaults are restored."""
+    from cy4 import _lib
+    L = _lib.lib()
+    ok = [(b"conv_cluster", 2), (b"conv_cluster", 1), (b"wgrad_cluster", 2), (b"wgrad_cluster", 1), (b"tma_store", 0), (b"tma_store", 1),
+          (b"kblocks_per_slot", 1), (b"kblocks_per_slot", 4), (b"wgrad_variant", 2), (b"wgrad_variant", 1), (b"conv_pair", 1), (b"conv_pair", 0),
+          (b"debug", 0)]
+    for name, value in ok:
+        assert L.cy4_set_option(name, value) == 0, (name, value)
+    for name, value in [(b"no_such_option", 1), (b"wgrad_cluster", 3), (b"wgrad_variant", 7)]:
+        assert L.cy4_set_option(name, value) < 0, (name, value)
+        assert L.cy4_last_error()
