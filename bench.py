@@ -210,19 +210,38 @@ def run_ours(args):
                 k2[0] += a.elapsed_time(b); k2[1] += fl; k2[2] += 1
             top_shapes = [{"kernel": n_, "cin_cout_k_s_ho": list(sh), "launches_per_step": v[2] // 2, "ms_per_step": round(v[0] / 2, 3),
                            "tflops": round(v[1] / (v[0] * 1e9), 1) if v[0] else 0.0}
-                          for (n_, sh), v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:24]]
+                          for (n_, sh), v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])]
         except Exception as e:      # noqa: BLE001 -- diagnostics must never cost the headline line
             top_shapes = [{"error": repr(e)[:200]}]
         conv_ms = sum(v[0] for v in agg.values()) / 2
         tc = {n: {"ms_per_step": v[0] / 2, "tflops": v[1] / (v[0] * 1e9) if v[0] else 0.0, "launches_per_step": v[2] // 2} for n, v in agg.items()}
         fwd = agg.get("cy4_conv_fwd", [1e-9, 0, 1])
         achieved = fwd[1] / (fwd[0] * 1e9)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_conv_fprop_traffic.json")
+        # dram read+write bytes per fprop launch: from this round's `ncu --set full` capture of the shipped kernel over the
+        # same workload (profiles/r2_conv_fprop_traffic.json, written by tools/ncu_summarise.py); null when no capture of
+        # the current kernel exists -- never a stale constant
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r2_conv_fprop_traffic.json")
         if os.path.exists(tpath) and args.cfg == "complex_yolov4" and B == 32:
-            traffic = json.load(open(tpath))["bytes_per_launch"]      # dram read+write per launch, ncu capture of the same workload
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("bytes_per_launch"), tj.get("source")
+        # ---- the whole forward (110 convs + BN/activation passes + routes + loss head), CUDA events: the north_star's
+        # ">= 40 % of tensor peak on the forward" is about THIS, not about the fprop launches alone
+        fwd_ms = None
+        try:
+            with torch.no_grad():
+                for _ in range(2):
+                    net(x, tg)
+                fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); fa.record()
+                for _ in range(5):
+                    net(x, tg)
+                fb.record(); torch.cuda.synchronize()
+                fwd_ms = fa.elapsed_time(fb) / 5
+        except Exception as e:      # noqa: BLE001
+            sys.stderr.write("forward-only timing failed: %r\n" % (e,))
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fprop launches)", "achieved": round(achieved, 1), "peak": pk["tf_sustained"],
-                "unit": "TFLOP/s", "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic,
+                "unit": "TFLOP/s", "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["src"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
                 "flops_per_step": fwd[1] / 2, "avg_launch_ms": fwd[0] / max(fwd[2], 1), "by_kernel": tc,
                 "top_layer_shapes": top_shapes, "conv_share_of_step": round(conv_ms / ms_per_step, 3)}
@@ -241,11 +260,11 @@ def run_ours(args):
                 cg.rgiou_pairs(pd, td_, True)
             b.record(); torch.cuda.synchronize()
             t = a.elapsed_time(b) / reps
-            if n == 100_000:        # the oracle port (C, one thread) on the same pairs, for the north_star's ">= 100x CPU" bar
+            if n == 100_000:        # the CPU legs on the same pairs, for the north_star's ">= 100x CPU" bar
                 from oracle import geometry as og
                 t0 = time.perf_counter(); og.rgiou_pairs(p_, t_, True); cpu_s = time.perf_counter() - t0
                 giou["cpu_port_pairs_per_s_1thread"] = round(n / cpu_s, 0)
-                giou["reference_python_pairs_per_s"] = "1152 (survey container, BASELINE.md section 4; the Python reference cannot run on the GPU box)"
+                giou["reference_python"] = reference_giou_rate(p_, t_)
             giou[str(n)] = {"us": round(t * 1e3, 2), "pairs_per_s": round(n / (t / 1e3), 0), "GBps": round(n * 56 / (t / 1e3) / 1e9, 1),
                             "hbm_frac": round(n * 56 / (t / 1e3) / 1e9 / pk["hbm_gbs"], 4)}
         # ---- the "next" rows built so far, outside the timed region; a failure here must
@@ -296,7 +315,11 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h_bytes, "last_loss": lval},
             "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps,
             "clocks": clk, "roofline": roof,
-            "fwd_tensor_frac_of_step_flops": None,
+            "forward_only": None if not fwd_ms else {
+                "ms": round(fwd_ms, 3), "tflops": round(GFLOP_FWD_PER_IMG.get(args.cfg, 0) * B * 1e-3 / (fwd_ms / 1e3), 1),
+                "frac_of_sustained_peak": round(GFLOP_FWD_PER_IMG.get(args.cfg, 0) * B * 1e-3 / (fwd_ms / 1e3) / pk["tf_sustained"], 4),
+                "what": "whole training-mode forward incl. BN/activation passes and the loss head, conv FLOPs only in the numerator"},
+            "library_baseline": library_baseline(),
             "step_tflops": round(3 * GFLOP_FWD_PER_IMG.get(args.cfg, 0) * B * 1e-3 / (ms_per_step / 1e3), 1),
             "rgiou_microbench": giou,
             "next_rows": nxt,
@@ -307,6 +330,40 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return result
+
+
+def library_baseline():
+    """Same-box PyTorch/cuDNN step of the conv stack (tools/cudnn_comparator.py), measured this round on a
+    B200 of this pool and committed under profiles/: context for the headline, not a bench leg."""
+    out = {}
+    for mode in ("fp16", "tf32"):
+        path = os.path.join(ROOT, "profiles", "r2_cudnn_comparator_%s.json" % mode)
+        if os.path.exists(path):
+            try:
+                out[mode] = json.load(open(path))
+            except Exception:       # noqa: BLE001
+                pass
+    return out or None
+
+
+def reference_giou_rate(pred, tgt, n=1000):
+    """iou_pred_vs_target_boxes(GIoU=True) of the UNMODIFIED reference on the first n pairs, host CPU."""
+    mods = reference_modules()
+    if mods is None:
+        return {"unavailable": "no oracle/_ref on this box"}
+    try:
+        import contextlib
+        torch.set_num_threads(1)       # the loop is Python-bound; one thread is the faster setting (SURVEY 8d)
+        p = torch.tensor(pred[:n]); t = torch.tensor(tgt[:n])
+        with contextlib.redirect_stdout(sys.stderr):
+            mods["iou"].iou_pred_vs_target_boxes(p[:8], t[:8], GIoU=True)
+            t0 = time.perf_counter()
+            mods["iou"].iou_pred_vs_target_boxes(p, t, GIoU=True)
+            dt = time.perf_counter() - t0
+        return {"pairs_per_s": round(n / dt, 1), "pairs_timed": n, "threads": 1,
+                "what": "utils.iou_rotated_boxes_utils.iou_pred_vs_target_boxes(GIoU=True), unmodified, torch CPU"}
+    except Exception as e:          # noqa: BLE001
+        return {"error": repr(e)[:200]}
 
 
 def usable_cores():
@@ -336,53 +393,113 @@ def workload_name(cfg, batch):
             "5 targets/img, GIoU on" % (cfg, batch))
 
 
-def cpu_step_baseline(cfg, budget_s=25.0, batch=2):
-    """The oracle port of the same training step on the host cores (plain PyTorch fp32 + the C
-    restatement of the rotated-box geometry), on a bounded sample: `batch` images per step."""
-    from cy4 import netdefs, synth
-    from cy4.darknet import Darknet
-    from oracle import darknet_oracle as do
-    cores = usable_cores()
-    torch.set_num_threads(cores)
-    path = netdefs.cfg_path(cfg)
-    torch.manual_seed(0)
-    sd = Darknet(path, True).state_dict()
-    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
-    blocks = do.parse_cfg(path)
-    x = synth.make_bev(batch)
-    tg = torch.tensor(synth.make_targets(batch, per_image=5, seed=4321))
-    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-3)
-    times = []
-    t_start = time.perf_counter()
-    while True:
+def reference_modules():
+    """The UNMODIFIED reference modules (oracle/_ref copy on the GPU box, /root/reference/src in the build container)
+    with the import stand-ins of oracle/ref_stubs.py, or None when no reference tree travelled with the snapshot."""
+    try:
+        from oracle import reference_loader as rl, ref_stubs
+        if not rl.available():
+            return None
+        kinds = ref_stubs.install()
+        mods = rl.load()
+        mods["kinds"] = kinds
+        mods["src"] = rl.REF_SRC
+        return mods
+    except Exception as e:      # noqa: BLE001 -- fall back to the port, and say so
+        sys.stderr.write("bench: reference modules unavailable (%r); timing the oracle port instead\n" % (e,))
+        return None
+
+
+class CpuStep:
+    """One training step of the hot path on the host cores: the reference's own Darknet(cfg).forward + backward + Adam
+    (kind "reference") when oracle/_ref is present, else the oracle port (kind "port")."""
+
+    def __init__(self, cfg, batch):
+        from cy4 import netdefs, synth
+        self.batch = batch
+        self.cores = usable_cores()
+        torch.set_num_threads(self.cores)
+        self.x = synth.make_bev(batch)
+        self.tg = torch.tensor(synth.make_targets(batch, per_image=5, seed=4321))
+        mods = reference_modules()
+        if mods is not None:
+            self.kind = "reference"
+            cfgfile = os.path.join(mods["src"], "config", "cfg", cfg + ".cfg")
+            torch.manual_seed(0)
+            self.model = mods["darknet"].Darknet(cfgfile=cfgfile, use_giou_loss=True).train()
+            self.opt = make_optimizer(self.model)
+            self.what = ("UNMODIFIED reference Darknet(%s.cfg).forward + loss.backward + Adam on the host CPU (shapely: %s)"
+                         % (cfg, mods["kinds"].get("shapely")))
+        else:
+            from cy4.darknet import Darknet
+            from oracle import darknet_oracle as do
+            self.kind = "port"
+            path = netdefs.cfg_path(cfg)
+            torch.manual_seed(0)
+            sd = Darknet(path, True).state_dict()
+            self.params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+            self.blocks = do.parse_cfg(path)
+            self.do = do
+            self.opt = torch.optim.Adam([p for p in self.params.values() if p.requires_grad], lr=1e-3)
+            self.what = "fp32 oracle port of the same step (torch CPU ops + C rotated-box geometry)"
+
+    def step(self):
         t0 = time.perf_counter()
-        loss, _, _ = do.forward(blocks, params, x, tg, True, True, update_running=True)
+        if self.kind == "reference":
+            loss, _ = self.model(self.x, self.tg)
+        else:
+            loss, _, _ = self.do.forward(self.blocks, self.params, self.x, self.tg, True, True, update_running=True)
         loss.backward()
-        opt.step(); opt.zero_grad()
-        times.append(time.perf_counter() - t0)
-        if (len(times) >= 2 and (time.perf_counter() - t_start > budget_s or len(times) >= 6)) or time.perf_counter() - t_start > 4 * budget_s:
-            break
+        self.opt.step(); self.opt.zero_grad()
+        return time.perf_counter() - t0
+
+
+def cpu_step_baseline(cfg, budget_s=25.0, batch=2):
+    """The same training step on the host cores, on a bounded sample: `batch` images per step, ~budget_s seconds."""
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):        # the reference prints while it builds the network
+        runner = CpuStep(cfg, batch)
+        times = []
+        t_start = time.perf_counter()
+        while True:
+            times.append(runner.step())
+            if (len(times) >= 2 and (time.perf_counter() - t_start > budget_s or len(times) >= 8)) or time.perf_counter() - t_start > 4 * budget_s:
+                break
     best = min(times[1:]) if len(times) > 1 else times[0]
-    return {"value": round(batch / best, 3), "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of bs=%d (same net, same loss, fp32 oracle port: torch CPU ops + C rotated-box geometry); "
-                      "best step after 1 warm-up" % (len(times), batch)}
+    return {"value": round(batch / best, 3), "unit": "img/s", "cores": runner.cores, "kind": runner.kind,
+            "sample": "%d steps of bs=%d of the bench workload (%s); best step after 1 warm-up" % (len(times), batch, runner.what)}
 
 
 def run_reference(args):
+    """`--impl reference`: W untimed + K timed steps of the reference's own CPU implementation of the step, each step a
+    bounded sample (bs=2) of the bench workload; `steps`, `warmup` and `ms_per_step` describe exactly what ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if os.environ.get("CY4_BENCH_TEST_TINY"):       # CPU unit test of the harness: tiny net, tiny budget
+    if os.environ.get("CY4_BENCH_TEST_TINY"):       # CPU unit test of the harness: tiny net
         args.cfg = "complex_yolov4_tiny"
-    base = cpu_step_baseline(args.cfg, budget_s=3.0 if os.environ.get("CY4_BENCH_TEST_TINY") else max(20.0, 6.0 * (args.steps + args.warmup)))
-    return {"impl": "reference", "metric": "BEV-images/sec training step (bs=32, 608x608)", "value": base["value"], "unit": "img/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(2e3 / base["value"], 1),
+    sample_bs = 2
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):        # the reference prints while it builds the network
+        runner = CpuStep(args.cfg, sample_bs)
+        for _ in range(args.warmup):
+            runner.step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            runner.step()
+        total = time.perf_counter() - t0
+    ms_per_step = total / max(args.steps, 1) * 1e3
+    value = round(sample_bs * args.steps / total, 3)
+    base = {"value": value, "unit": "img/s", "cores": runner.cores, "kind": runner.kind,
+            "sample": "%d timed steps (+%d warm-up) of bs=%d of the bench workload: %s" % (args.steps, args.warmup, sample_bs, runner.what)}
+    return {"impl": "reference", "metric": "BEV-images/sec training step (bs=32, 608x608)", "value": value, "unit": "img/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": workload_name(args.cfg, args.batch), "global_batch": args.batch * world, "parallelism": "host cpu",
-                       "sample": "the same step on the host cores, bounded to bs=2 per step (see cpu_baseline.sample)"},
+                       "sample": "each step is a bounded sample of that workload: bs=%d on the host cores (img/s is what is compared)" % sample_bs},
             "cpu_baseline": base,
-            "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def main():

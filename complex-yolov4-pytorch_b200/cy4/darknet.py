@@ -284,7 +284,8 @@ class Darknet(nn.Module):
         def take(t):
             nonlocal start
             n = t.numel()
-            t.data.copy_(torch.from_numpy(buf[start:start + n]).reshape(t.shape))
+            with torch.no_grad():         # in-place copy that bumps t._version: the engine re-packs its fp16 weights
+                t.copy_(torch.from_numpy(buf[start:start + n]).reshape(t.shape))
             start += n
 
         ind = -2

@@ -73,6 +73,20 @@ class View:
         lo, hi = self.off, self.off + self.C
         return any(a < hi and lo < b for a, b in self.st.gwritten)
 
+    def zero_unwritten(self):
+        """Zero-fills the channel intervals of this view's gradient that no consumer has written in this backward
+        pass (the .grad buffers persist across steps, so an uncovered interval would otherwise hold stale data)."""
+        lo, hi = self.off, self.off + self.C
+        st = self.st
+        pos = lo
+        for a, b in sorted((max(a, lo), min(b, hi)) for a, b in st.gwritten if a < hi and lo < b):
+            if a > pos:
+                st.grad[..., pos:a].zero_()
+            pos = max(pos, b)
+        if pos < hi:
+            st.grad[..., pos:hi].zero_()
+            st.gwritten.append((lo, hi))
+
     def grad_mode(self):
         """Call before writing this view's gradient.  Returns 1 if the kernel must accumulate, 0 if it
         may overwrite; zero-fills the not-yet-written part when the view is only partly covered."""
@@ -198,7 +212,9 @@ class StepEngine:
             with torch.cuda.graph(gs["bwd"]):
                 gs["grads"] = plan.backward(gs["g"])
         gs["bwd"].replay()
-        return gs["grads"]
+        # the captured gradient tensors are static graph memory: hand autograd private copies (it may keep what it gets
+        # as .grad, and the next replay overwrites the static buffers)
+        return [None if t is None else t.clone() for t in gs["grads"]]
 
 
 class Plan:
@@ -648,12 +664,16 @@ class Plan:
             self._call(L.cy4_absmax_f32, head["dP"].data_ptr(), head["dP"].numel(), self.gscale[2:].data_ptr(), st)
             head["has_grad"] = True
         self._call(L.cy4_make_scale, self.gscale[2:].data_ptr(), self.scale_target, self.gscale.data_ptr(), st)
-        # param gradient buffer (fresh each backward: autograd may keep what we return)
+        # The unpack launch writes every conv gradient into the persistent flat buffer (its item table holds the
+        # addresses); what autograd receives are slices of a FRESH copy made after the unpack: AccumulateGrad keeps
+        # the tensors it is handed as .grad (it looks at the view's own use count, not at the base buffer's), so
+        # returning views of a persistent buffer would alias .grad with the next backward's output and break
+        # gradient accumulation (train.py accumulates over `subdivisions` backward calls per optimizer step).
         if getattr(self, "gw_flat", None) is None:
-            # persistent: autograd clones what we return because we keep a reference (safe with grad accumulation)
             self.gw_flat = torch.zeros(self.gw_numel, device=dev, dtype=torch.float32)
         gw_flat = self.gw_flat
         grads = {}
+        self._wslices = []
 
         events = {}
         for rec in self.convs:
@@ -711,6 +731,9 @@ class Plan:
                 self._call(L.cy4_upsample2x_bwd, out.gptr, out.ld, src.gptr, src.ld, B, Hi, Wi, src.C, acc, st)
 
         self._unpack_all(st)
+        fresh = gw_flat.clone()
+        for w, off in self._wslices:
+            grads[id(w)] = fresh[off:off + w.numel()].view_as(w)
         # BN parameter gradients: d beta = sum dz, d gamma = sum dz*xhat (both carry the loss scale)
         gbn = self.dbn * self.gscale[1]
         for rec in self.convs:
@@ -754,6 +777,7 @@ class Plan:
             A, Y = rec["A"], rec["Y"]
             if not A.grad_has():
                 return                                   # no gradient reaches this layer
+            A.zero_unwritten()                           # e.g. only a `groups` slice of A was consumed
             c0 = rec["coff"]
             q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
             sdz, sdzx = self.dbn[0, c0:].data_ptr(), self.dbn[1, c0:].data_ptr()
@@ -795,4 +819,4 @@ class Plan:
             d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, ldy, co.CONV_ZERO_ACC)
             self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), st)
             # (unpacked for all layers by one launch at the end of backward)
-        grads[id(conv.weight)] = gw
+        self._wslices.append((conv.weight, rec["woff"]))

@@ -9,7 +9,8 @@ __all__ = ['parse_cfg', 'print_cfg', 'load_conv', 'load_conv_bn', 'save_conv', '
 
 def _take(buf, start, t):
     n = t.numel()
-    t.data.copy_(torch.from_numpy(buf[start:start + n]).reshape(t.shape))
+    with torch.no_grad():         # in-place copy that bumps t._version: the engine re-packs its fp16 weights
+        t.copy_(torch.from_numpy(buf[start:start + n]).reshape(t.shape))
     return start + n
 
 

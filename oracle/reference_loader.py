@@ -1,14 +1,17 @@
-"""Import the UNMODIFIED reference modules from /root/reference/src (build container only).
+"""Import the UNMODIFIED reference modules: from /root/reference/src in the build container, else from the
+byte-identical copy oracle/_ref/src that build() makes there (oracle/make_ref.py; git-ignored, travels to the
+GPU box with the snapshot).
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box: nothing that runs
-there may call this.  Used by oracle/gen_golden.py and by the optional live cross-checks in
-tests/ (skipped when the reference tree is absent).
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py, the live cross-checks in tests/ (skipped
+when no reference tree is available), bench.py --impl reference and the GIoU micro-benchmark's CPU leg.
 """
 import importlib
 import os
 import sys
 
-REF_SRC = "/root/reference/src"
+from . import make_ref
+
+REF_SRC = make_ref.ref_src() or make_ref.SRC
 
 
 def available():

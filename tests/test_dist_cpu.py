@@ -85,7 +85,8 @@ def test_ddp_single_node_function_gloo(tmp_path):
 
 def test_bench_reference_arm_under_torchrun(tmp_path):
     """`bench.py --impl reference` launched like the driver does for N=2: rank 0 prints ONE JSON line
-    (CPU oracle port on a bounded sample), the other rank exits 0 without output."""
+    (the reference's own CPU step on a bounded sample -- the unmodified reference when oracle/_ref or /root/reference is
+    present, else the oracle port), the other rank exits 0 without output; `steps` is what really ran."""
     env = dict(os.environ, CY4_BENCH_TEST_TINY="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
@@ -94,5 +95,6 @@ def test_bench_reference_arm_under_torchrun(tmp_path):
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["value"] > 0 and d["unit"] == "img/s"
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["unit"] == "img/s" and d["steps"] == 1 and d["warmup"] == 0
+    assert abs(d["ms_per_step"] * d["value"] / 1e3 - 2.0) < 0.05          # ms_per_step is the bs=2 sample step that was timed

@@ -290,3 +290,50 @@ def test_elementwise_kernels_vs_torch():
     gin = torch.zeros_like(x16)
     _lib.check(L.cy4_upsample2x_bwd(up.data_ptr(), 64, gin.data_ptr(), 64, 2, 19, 19, 64, 0, st))
     assert (gin.float() - 4 * x16.float()).abs().max().item() < 2e-2
+
+
+def test_gradient_accumulation_and_weight_reload():
+    """train.py accumulates gradients over `subdivisions` backward calls per optimizer step (reference
+    src/train.py:212-217): two backwards without zero_grad must leave p.grad == g1 + g2 (the engine hands autograd
+    private gradient tensors, never views of its persistent buffers), and zero_grad(set_to_none=False) must not
+    double anything.  Also: weights changed in place after a forward (load_weights / load_state_dict) are re-packed."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    torch.manual_seed(0)
+    model = Darknet(netdefs.cfg_path("complex_yolov4_tiny"), True).cuda().train()
+    xs = [synth.make_bev(2, img_size=160, seed=s).cuda() for s in (1, 2)]
+    tgs = [torch.tensor(synth.make_targets(2, per_image=3, seed=s, img_size=160, strides=(16, 32))).cuda() for s in (3, 4)]
+    # BN batch statistics depend only on the batch, so the two single-batch gradients are reproducible up to atomics
+    singles = []
+    for x, tg in zip(xs, tgs):
+        model.zero_grad(set_to_none=True)
+        loss, _ = model(x, tg)
+        loss.backward()
+        singles.append({n: p.grad.clone() for n, p in model.named_parameters()})
+    model.zero_grad(set_to_none=True)
+    for x, tg in zip(xs, tgs):
+        loss, _ = model(x, tg)
+        loss.backward()
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        want = singles[0][n] + singles[1][n]
+        tol = 2e-3 * want.abs().max().item() + 1e-7          # fp32 atomics order only
+        assert (p.grad - want).abs().max().item() <= tol, n
+    # zero_grad(set_to_none=False) keeps the .grad tensors: the next backward must ADD into zeros, not alias them
+    model.zero_grad(set_to_none=False)
+    loss, _ = model(xs[0], tgs[0])
+    loss.backward()
+    for n, p in model.named_parameters():
+        want = singles[0][n]
+        assert (p.grad - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-7, n
+    # in-place weight change after a forward: the fp16 packs must follow
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    l0 = model(xs[0], tgs[0])[0].item()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 4:
+                p.mul_(0.5)
+    l1 = model(xs[0], tgs[0])[0].item()
+    model.load_state_dict(sd)
+    l2 = model(xs[0], tgs[0])[0].item()
+    assert abs(l0 - l2) <= 1e-4 * abs(l0) and abs(l0 - l1) > 1e-4 * abs(l0)
