@@ -186,123 +186,125 @@ def run_ours(args):
         pk = peaks()
         ms_per_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total / 1e3)
-        # ---- roofline pass: CUDA-event timing of every tensor-core conv launch for 2 steps
-        plan = net._engine.plan
-        net.use_cuda_graph = False          # events around individual launches need eager launches
-        plan.prof = []
-        for _ in range(2):                  # on the bare module: no collective may run on rank 0 alone
-            l_, _o = net(x, tg)
-            l_.backward()
-            opt.step()
-            opt.zero_grad(set_to_none=True)
-        torch.cuda.synchronize()
-        prof, plan.prof = plan.prof, None
-        agg = {}
-        for name, a, b, fl, shape in prof:
-            t = a.elapsed_time(b)
-            k = agg.setdefault(name, [0.0, 0.0, 0])
-            k[0] += t; k[1] += fl; k[2] += 1
-        # per layer shape (Cin, Cout, k, stride, Ho): where the tensor-core time goes, for the next optimisation round
-        try:
-            by_shape = {}
+        roof, giou, nxt, fwd_ms = None, None, None, None
+        if not args.no_roofline:
+            # ---- roofline pass: CUDA-event timing of every tensor-core conv launch for 2 steps
+            plan = net._engine.plan
+            net.use_cuda_graph = False          # events around individual launches need eager launches
+            plan.prof = []
+            for _ in range(2):                  # on the bare module: no collective may run on rank 0 alone
+                l_, _o = net(x, tg)
+                l_.backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+            prof, plan.prof = plan.prof, None
+            agg = {}
             for name, a, b, fl, shape in prof:
-                k2 = by_shape.setdefault((name, tuple(shape)), [0.0, 0.0, 0])
-                k2[0] += a.elapsed_time(b); k2[1] += fl; k2[2] += 1
-            top_shapes = [{"kernel": n_, "cin_cout_k_s_ho": list(sh), "launches_per_step": v[2] // 2, "ms_per_step": round(v[0] / 2, 3),
-                           "tflops": round(v[1] / (v[0] * 1e9), 1) if v[0] else 0.0}
-                          for (n_, sh), v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])]
-        except Exception as e:      # noqa: BLE001 -- diagnostics must never cost the headline line
-            top_shapes = [{"error": repr(e)[:200]}]
-        conv_ms = sum(v[0] for v in agg.values()) / 2
-        tc = {n: {"ms_per_step": v[0] / 2, "tflops": v[1] / (v[0] * 1e9) if v[0] else 0.0, "launches_per_step": v[2] // 2} for n, v in agg.items()}
-        fwd = agg.get("cy4_conv_fwd", [1e-9, 0, 1])
-        achieved = fwd[1] / (fwd[0] * 1e9)
-        # dram read+write bytes per fprop launch: from this round's `ncu --set full` capture of the shipped kernel over the
-        # same workload (profiles/r2_conv_fprop_traffic.json, written by tools/ncu_summarise.py); null when no capture of
-        # the current kernel exists -- never a stale constant
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r2_conv_fprop_traffic.json")
-        if os.path.exists(tpath) and args.cfg == "complex_yolov4" and B == 32:
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj.get("bytes_per_launch"), tj.get("source")
-        # ---- the whole forward (110 convs + BN/activation passes + routes + loss head), CUDA events: the north_star's
-        # ">= 40 % of tensor peak on the forward" is about THIS, not about the fprop launches alone
-        fwd_ms = None
-        try:
-            with torch.no_grad():
+                t = a.elapsed_time(b)
+                k = agg.setdefault(name, [0.0, 0.0, 0])
+                k[0] += t; k[1] += fl; k[2] += 1
+            # per layer shape (Cin, Cout, k, stride, Ho): where the tensor-core time goes, for the next optimisation round
+            try:
+                by_shape = {}
+                for name, a, b, fl, shape in prof:
+                    k2 = by_shape.setdefault((name, tuple(shape)), [0.0, 0.0, 0])
+                    k2[0] += a.elapsed_time(b); k2[1] += fl; k2[2] += 1
+                top_shapes = [{"kernel": n_, "cin_cout_k_s_ho": list(sh), "launches_per_step": v[2] // 2, "ms_per_step": round(v[0] / 2, 3),
+                               "tflops": round(v[1] / (v[0] * 1e9), 1) if v[0] else 0.0}
+                              for (n_, sh), v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])]
+            except Exception as e:      # noqa: BLE001 -- diagnostics must never cost the headline line
+                top_shapes = [{"error": repr(e)[:200]}]
+            conv_ms = sum(v[0] for v in agg.values()) / 2
+            tc = {n: {"ms_per_step": v[0] / 2, "tflops": v[1] / (v[0] * 1e9) if v[0] else 0.0, "launches_per_step": v[2] // 2} for n, v in agg.items()}
+            fwd = agg.get("cy4_conv_fwd", [1e-9, 0, 1])
+            achieved = fwd[1] / (fwd[0] * 1e9)
+            # dram read+write bytes per fprop launch: from this round's `ncu --set full` capture of the shipped kernel over the
+            # same workload (profiles/r2_conv_fprop_traffic.json, written by tools/ncu_summarise.py); null when no capture of
+            # the current kernel exists -- never a stale constant
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r2_conv_fprop_traffic.json")
+            if os.path.exists(tpath) and args.cfg == "complex_yolov4" and B == 32:
+                tj = json.load(open(tpath))
+                traffic, traffic_src = tj.get("bytes_per_launch"), tj.get("source")
+            # ---- the whole forward (110 convs + BN/activation passes + routes + loss head), CUDA events: the north_star's
+            # ">= 40 % of tensor peak on the forward" is about THIS, not about the fprop launches alone
+            fwd_ms = None
+            try:
+                with torch.no_grad():
+                    for _ in range(2):
+                        net(x, tg)
+                    fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize(); fa.record()
+                    for _ in range(5):
+                        net(x, tg)
+                    fb.record(); torch.cuda.synchronize()
+                    fwd_ms = fa.elapsed_time(fb) / 5
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write("forward-only timing failed: %r\n" % (e,))
+            roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fprop launches)", "achieved": round(achieved, 1), "peak": pk["tf_sustained"],
+                    "unit": "TFLOP/s", "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": pk["src"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
+                    "flops_per_step": fwd[1] / 2, "avg_launch_ms": fwd[0] / max(fwd[2], 1), "by_kernel": tc,
+                    "top_layer_shapes": top_shapes, "conv_share_of_step": round(conv_ms / ms_per_step, 3)}
+            # ---- rotated-GIoU microbench (BASELINE config 4): 100k pairs (latency) and 10^7 pairs (bandwidth)
+            from cy4 import geometry as cg
+            giou = {}
+            for n in (100_000, 10_000_000):
+                p_, t_ = synth.make_pairs(n, seed=7)
+                pd, td_ = torch.tensor(p_, device=dev), torch.tensor(t_, device=dev)
+                for _ in range(3):
+                    cg.rgiou_pairs(pd, td_, True)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); a.record()
+                reps = 20 if n <= 100_000 else 5
+                for _ in range(reps):
+                    cg.rgiou_pairs(pd, td_, True)
+                b.record(); torch.cuda.synchronize()
+                t = a.elapsed_time(b) / reps
+                if n == 100_000:        # the CPU legs on the same pairs, for the north_star's ">= 100x CPU" bar
+                    from oracle import geometry as og
+                    t0 = time.perf_counter(); og.rgiou_pairs(p_, t_, True); cpu_s = time.perf_counter() - t0
+                    giou["cpu_port_pairs_per_s_1thread"] = round(n / cpu_s, 0)
+                    giou["reference_python"] = reference_giou_rate(p_, t_)
+                giou[str(n)] = {"us": round(t * 1e3, 2), "pairs_per_s": round(n / (t / 1e3), 0), "GBps": round(n * 56 / (t / 1e3) / 1e9, 1),
+                                "hbm_frac": round(n * 56 / (t / 1e3) / 1e9 / pk["hbm_gbs"], 4)}
+            # ---- the "next" rows built so far, outside the timed region; a failure here must
+            # not cost the headline line, so each is guarded and reports its error instead
+            nxt = {}
+            try:
+                from cy4 import evalops
+                tgs = synth.make_targets(B, per_image=8, seed=11)
+                dets_h = synth.make_detections(B, tgs, n_rows=22743, dup=8, clutter=150, seed=3)
+                pd_ = torch.tensor(dets_h, device=dev)
+                tpx = tgs.copy(); tpx[:, 2:6] *= 608
+                td2 = torch.tensor(tpx, device=dev)
                 for _ in range(2):
-                    net(x, tg)
-                fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize(); fa.record()
+                    dd = evalops.nms_v2(pd_, 0.5, 0.4); evalops.match(dd, td2, 0.5)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); a.record()
                 for _ in range(5):
-                    net(x, tg)
-                fb.record(); torch.cuda.synchronize()
-                fwd_ms = fa.elapsed_time(fb) / 5
-        except Exception as e:      # noqa: BLE001
-            sys.stderr.write("forward-only timing failed: %r\n" % (e,))
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fprop launches)", "achieved": round(achieved, 1), "peak": pk["tf_sustained"],
-                "unit": "TFLOP/s", "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": pk["src"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
-                "flops_per_step": fwd[1] / 2, "avg_launch_ms": fwd[0] / max(fwd[2], 1), "by_kernel": tc,
-                "top_layer_shapes": top_shapes, "conv_share_of_step": round(conv_ms / ms_per_step, 3)}
-        # ---- rotated-GIoU microbench (BASELINE config 4): 100k pairs (latency) and 10^7 pairs (bandwidth)
-        from cy4 import geometry as cg
-        giou = {}
-        for n in (100_000, 10_000_000):
-            p_, t_ = synth.make_pairs(n, seed=7)
-            pd, td_ = torch.tensor(p_, device=dev), torch.tensor(t_, device=dev)
-            for _ in range(3):
-                cg.rgiou_pairs(pd, td_, True)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); a.record()
-            reps = 20 if n <= 100_000 else 5
-            for _ in range(reps):
-                cg.rgiou_pairs(pd, td_, True)
-            b.record(); torch.cuda.synchronize()
-            t = a.elapsed_time(b) / reps
-            if n == 100_000:        # the CPU legs on the same pairs, for the north_star's ">= 100x CPU" bar
-                from oracle import geometry as og
-                t0 = time.perf_counter(); og.rgiou_pairs(p_, t_, True); cpu_s = time.perf_counter() - t0
-                giou["cpu_port_pairs_per_s_1thread"] = round(n / cpu_s, 0)
-                giou["reference_python"] = reference_giou_rate(p_, t_)
-            giou[str(n)] = {"us": round(t * 1e3, 2), "pairs_per_s": round(n / (t / 1e3), 0), "GBps": round(n * 56 / (t / 1e3) / 1e9, 1),
-                            "hbm_frac": round(n * 56 / (t / 1e3) / 1e9 / pk["hbm_gbs"], 4)}
-        # ---- the "next" rows built so far, outside the timed region; a failure here must
-        # not cost the headline line, so each is guarded and reports its error instead
-        nxt = {}
-        try:
-            from cy4 import evalops
-            tgs = synth.make_targets(B, per_image=8, seed=11)
-            dets_h = synth.make_detections(B, tgs, n_rows=22743, dup=8, clutter=150, seed=3)
-            pd_ = torch.tensor(dets_h, device=dev)
-            tpx = tgs.copy(); tpx[:, 2:6] *= 608
-            td2 = torch.tensor(tpx, device=dev)
-            for _ in range(2):
-                dd = evalops.nms_v2(pd_, 0.5, 0.4); evalops.match(dd, td2, 0.5)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); a.record()
-            for _ in range(5):
-                dd = evalops.nms_v2(pd_, 0.5, 0.4); evalops.match(dd, td2, 0.5)
-            b.record(); torch.cuda.synchronize()
-            nxt["f1_rotated_nms_and_matching"] = {"ms_per_batch": round(a.elapsed_time(b) / 5, 3), "batch": B, "rows_per_image": 22743,
-                                                  "candidates_per_image": int((dets_h[0, :, 6] >= 0.5).sum())}
-        except Exception as e:      # noqa: BLE001
-            nxt["f1_rotated_nms_and_matching"] = {"error": repr(e)[:300]}
-        try:
-            from cy4 import bevops
-            clouds = [torch.tensor(synth.make_point_cloud(120000, seed=100 + i, ties=False), device=dev) for i in range(B)]
-            for _ in range(2):
-                bevops.rasterize(clouds)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); a.record()
-            for _ in range(5):
-                bevops.rasterize(clouds)
-            b.record(); torch.cuda.synchronize()
-            t_ = a.elapsed_time(b) / 5
-            nxt["f3_lidar_to_bev"] = {"ms_per_batch": round(t_, 3), "batch": B, "points_per_frame": 120000,
-                                      "algorithmic_GBps": round(B * (120000 * 16 + 3 * 608 * 608 * 4) / (t_ / 1e3) / 1e9, 1)}
-        except Exception as e:      # noqa: BLE001
-            nxt["f3_lidar_to_bev"] = {"error": repr(e)[:300]}
+                    dd = evalops.nms_v2(pd_, 0.5, 0.4); evalops.match(dd, td2, 0.5)
+                b.record(); torch.cuda.synchronize()
+                nxt["f1_rotated_nms_and_matching"] = {"ms_per_batch": round(a.elapsed_time(b) / 5, 3), "batch": B, "rows_per_image": 22743,
+                                                      "candidates_per_image": int((dets_h[0, :, 6] >= 0.5).sum())}
+            except Exception as e:      # noqa: BLE001
+                nxt["f1_rotated_nms_and_matching"] = {"error": repr(e)[:300]}
+            try:
+                from cy4 import bevops
+                clouds = [torch.tensor(synth.make_point_cloud(120000, seed=100 + i, ties=False), device=dev) for i in range(B)]
+                for _ in range(2):
+                    bevops.rasterize(clouds)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); a.record()
+                for _ in range(5):
+                    bevops.rasterize(clouds)
+                b.record(); torch.cuda.synchronize()
+                t_ = a.elapsed_time(b) / 5
+                nxt["f3_lidar_to_bev"] = {"ms_per_batch": round(t_, 3), "batch": B, "points_per_frame": 120000,
+                                          "algorithmic_GBps": round(B * (120000 * 16 + 3 * 608 * 608 * 4) / (t_ / 1e3) / 1e9, 1)}
+            except Exception as e:      # noqa: BLE001
+                nxt["f3_lidar_to_bev"] = {"error": repr(e)[:300]}
         result = {
             "metric": "BEV-images/sec training step (bs=32, 608x608)", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,

@@ -50,7 +50,8 @@ def hot(rep, out):
         ("regs", "launch__registers_per_thread", 1),
         ("smem_KB", "launch__shared_mem_per_block_dynamic", None),
     ]
-    tensor_keys = [h for h in hdr if "tensor" in h and "pct_of_peak" in h]
+    tensor_keys = [h for h in hdr if "pipe_tensor_cycles_active" in h and "pct_of_peak" in h] or \
+                  [h for h in hdr if "pipe_tensor" in h and "pct_of_peak" in h]
     stall_keys = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")] or \
                  [h for h in hdr if h.startswith("smsp__average_warp_latency_issue_stalled")]
     lines = ["# ncu --set full, shipped kernels on bench-sized operands (tools/ncu_targets.py), B200, --clock-control none",
@@ -119,8 +120,8 @@ def step(path, out):
     tot = sum(a.get("gpu__time_duration.sum", 0) for a in agg.values())
     txt = ["# ncu metric pass over ONE training step (complex_yolov4, bs=32): last complete step of %s" % os.path.basename(path),
            "# serialised / cold-cache durations: compare SHARES, not absolutes. DRAM bytes are per-step totals.",
-           "", "| kernel | launches | sum dur ms | share | DRAM read GB | DRAM write GB | DRAM GB/s over its own time | tensor-pipe % (time-weighted) |", "|---|---|---|---|---|---|---|---|"]
-    tkey = next((m for a in agg.values() for m in a if "tensor" in m and "pct" in m), None)
+           "", "| kernel | launches | sum dur ms | share | DRAM read GB | DRAM write GB | DRAM GB/s over its own time | tensor-pipe % active (mean over launches) |", "|---|---|---|---|---|---|---|---|"]
+    tkey = next((m for a in agg.values() for m in a if "pipe_tensor_cycles_active" in m and "pct" in m), None)
     for nm, a in sorted(agg.items(), key=lambda kv: -kv[1].get("gpu__time_duration.sum", 0)):
         d = a.get("gpu__time_duration.sum", 0.0)
         rd, wr = a.get("dram__bytes_read.sum", 0.0), a.get("dram__bytes_write.sum", 0.0)
