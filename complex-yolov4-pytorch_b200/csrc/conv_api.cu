@@ -39,6 +39,7 @@ struct GenericConv {
     int omap, OH, OW, ostep, oh0, ow0;
     const float *bias; float *ch_sum, *ch_sqsum;
     int a_matrix;
+    int epi_mode, epi_act; const float *epi_scale, *epi_shift; const void *side; int64_t ld_side;   // fused epilogue (conv_tc.cuh)
 };
 
 static int run_generic(const GenericConv &g, cudaStream_t st)
@@ -62,6 +63,8 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     p.y = g.y; p.ldy = g.ldy; p.flags = g.flags;
     p.omap = g.omap; p.OH = g.OH; p.OW = g.OW; p.ostep = g.ostep; p.oh0 = g.oh0; p.ow0 = g.ow0;
     p.bias = g.bias; p.ch_sum = g.ch_sum; p.ch_sqsum = g.ch_sqsum;
+    p.epi_mode = g.epi_mode; p.epi_act = g.epi_act; p.epi_scale = g.epi_scale; p.epi_shift = g.epi_shift;
+    p.side = g.side; p.ld_side = g.ld_side;
     if (p.M <= 0) return 0;
     const int swz = p.kchunk * 2;
     alignas(64) CUtensorMap tmA, tmB;
@@ -75,7 +78,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     // clusters of 2 CTAs share each weight slab through TMA multicast (halves the L2 -> SM weight traffic)
     p.cluster = (p.tiles_m >= 2 && g_cluster >= 2) ? 2 : 1;
     if (g_cluster >= 4 && p.tiles_m >= 8 && p.block_n >= 64) p.cluster = 4;
-    const bool pair = g_conv_pair && conv_pair_eligible(p);
+    const bool pair = g_conv_pair && conv_pair_eligible(p) && p.epi_mode == EPI_NONE;
     if (pair) p.cluster = 2;             // weight box of block_n / 2 rows: each CTA of the pair loads its half
     rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n / p.cluster, swz, 0);
     if (rc) return rc;
@@ -180,7 +183,7 @@ __global__ void pack_batched_kernel(const cy4_pack_item *__restrict__ items)
             const int64_t r = i / Cin;
             const int tap = (int)(r % kk);
             const int co = (int)(r / kk);
-            out[i] = __float2half_rn(co < Cout ? w[((int64_t)co * Cin + ci) * kk + tap] : 0.f);
+            out[i] = __float2half_rn(co < Cout ? w[((int64_t)co * Cin + ci) * kk + tap] * (it.fold_scale ? __ldg(it.fold_scale + co) : 1.f) : 0.f);
         }
     }
     if (it.w_dgrad) {                       // [cin_pad][r][s][cout_pad]
@@ -260,8 +263,10 @@ int cy4_set_option(const char *name, int value)
     return -1;
 }
 
-int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias, float *ch_sum,
-                 float *ch_sqsum, void *stream)
+struct EpiArgs { int mode, act; const float *scale, *shift; const void *side; int64_t ld_side; };
+
+static int conv_fwd_impl(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias, float *ch_sum,
+                         float *ch_sqsum, const EpiArgs *epi, void *stream)
 {
     if (check_conv_desc(d, "cy4_conv_fwd")) return -1;
     CY4_CHECK_ARG(x && w_fprop && y, "cy4_conv_fwd: null pointer");
@@ -288,10 +293,46 @@ int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, voi
     g.bias = bias; g.ch_sum = ch_sum; g.ch_sqsum = ch_sqsum;
     g.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
     if (g.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_fwd: matrix mode needs a 1x1/s1/p0 conv");
+    if (epi) { g.epi_mode = epi->mode; g.epi_act = epi->act; g.epi_scale = epi->scale; g.epi_shift = epi->shift; g.side = epi->side; g.ld_side = epi->ld_side; }
     return run_generic(g, (cudaStream_t)stream);
 }
 
+int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias, float *ch_sum,
+                 float *ch_sqsum, void *stream)
+{
+    return conv_fwd_impl(d, x, w_fprop, y, bias, ch_sum, ch_sqsum, nullptr, stream);
+}
+
+int cy4_conv_fwd_fused(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *shift, int act,
+                       const void *residual, int64_t ldr, void *stream)
+{
+    CY4_CHECK_ARG(d && shift && act >= 0 && act <= 2, "cy4_conv_fwd_fused: bad argument");
+    CY4_CHECK_ARG(!(d->flags & (CY4_CONV_OUT_F32 | CY4_CONV_STATS | CY4_CONV_ACCUM)), "cy4_conv_fwd_fused: fp16 output without statistics / accumulation only");
+    CY4_CHECK_ARG(d->Cout % 32 == 0, "cy4_conv_fwd_fused: Cout must be a multiple of 32");
+    CY4_CHECK_ARG(!residual || (ldr % 8 == 0 && ldr >= d->Cout), "cy4_conv_fwd_fused: residual ld");
+    const EpiArgs e = {EPI_FWD_ACT, act, nullptr, shift, residual, ldr};
+    return conv_fwd_impl(d, x, w_fprop, y, nullptr, nullptr, nullptr, &e, stream);
+}
+
+static int conv_dgrad_impl(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, const EpiArgs *epi, float *s_dz,
+                           float *s_dzy, void *stream);
+
 int cy4_conv_dgrad(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, void *stream)
+{
+    return conv_dgrad_impl(d, dy, w_dgrad, dx, nullptr, nullptr, nullptr, stream);
+}
+
+int cy4_conv_dgrad_fused(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, const void *y_producer, int64_t ldyp,
+                         const float *scale, const float *shift, int act, float *sum_dz, float *sum_dzy, void *stream)
+{
+    CY4_CHECK_ARG(d && y_producer && scale && shift && sum_dz && sum_dzy && act >= 0 && act <= 2, "cy4_conv_dgrad_fused: bad argument");
+    CY4_CHECK_ARG(ldyp % 8 == 0 && ldyp >= d->Cin, "cy4_conv_dgrad_fused: producer ld");
+    const EpiArgs e = {EPI_BWD_DZ, act, scale, shift, y_producer, ldyp};
+    return conv_dgrad_impl(d, dy, w_dgrad, dx, &e, sum_dz, sum_dzy, stream);
+}
+
+static int conv_dgrad_impl(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, const EpiArgs *epi, float *s_dz,
+                           float *s_dzy, void *stream)
 {
     if (check_conv_desc(d, "cy4_conv_dgrad")) return -1;
     CY4_CHECK_ARG(dy && w_dgrad && dx, "cy4_conv_dgrad: null pointer");
@@ -305,6 +346,10 @@ int cy4_conv_dgrad(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, 
     g.N = d->Cin;
     g.y = dx; g.ldy = d->ldx;
     g.flags = (d->flags & CY4_CONV_ACCUM) ? CONV_F_ACCUM : 0;
+    if (epi) {
+        g.epi_mode = epi->mode; g.epi_act = epi->act; g.epi_scale = epi->scale; g.epi_shift = epi->shift; g.side = epi->side; g.ld_side = epi->ld_side;
+        g.flags |= CONV_F_STATS; g.ch_sum = s_dz; g.ch_sqsum = s_dzy;
+    }
     if (d->stride == 1) {
         CY4_CHECK_ARG(d->pad == k / 2 && (k & 1), "cy4_conv_dgrad: stride 1 needs odd k and pad = k/2");
         // dx[h] = sum_r dy[h + pad - r] w[r]: base = h + lower, offset o = k-1-r

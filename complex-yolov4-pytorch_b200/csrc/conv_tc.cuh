@@ -13,6 +13,20 @@ enum : uint32_t {
     CONV_F_TMA_OUT = 16u,  // internal: fp16 tile staged in swizzled smem and written with TMA stores
 };
 
+// Fused epilogues (ConvKParams::epi_mode).  Both apply per-output-channel parameters and read a "side" fp16 tensor with
+// the output's row mapping.
+enum : int {
+    EPI_NONE = 0,
+    // y = act(acc + shift[n]) (+ side[m, n]): eval-mode inference with BatchNorm folded into the weights (scale) and this
+    // shift; `side` is the residual of a fused shortcut.  Reference: darknet2pytorch.py:247-278 with model.eval().
+    EPI_FWD_ACT = 1,
+    // Input gradient fused with the FIRST pass of the producer's BatchNorm/activation backward: v = acc (+ old gradient
+    // when CONV_F_ACCUM), z = scale[n] * side[m, n] + shift[n] (side = the producer's raw conv output Y),
+    // dz = v * act'(z) is stored instead of v, and sum_m dz / sum_m dz * Y are accumulated into ch_sum / ch_sqsum
+    // (what cy4_bn_act_bwd_reduce computes in a separate pass over the tensor).
+    EPI_BWD_DZ = 2,
+};
+
 constexpr int kMaxTaps = 16;
 
 struct ConvKParams {
@@ -35,6 +49,10 @@ struct ConvKParams {
     int omap, OH, OW, ostep, oh0, ow0;   // strided output-row mapping (stride-2 dgrad parity classes)
     const float *bias; float *ch_sum, *ch_sqsum;
     uint32_t flags;
+    // fused epilogue
+    int epi_mode, epi_act;
+    const float *epi_scale, *epi_shift;  // per output channel
+    const void *side; int64_t ld_side;   // fp16 [rows, ld_side], same row mapping as y
 };
 
 int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,

@@ -21,7 +21,7 @@ PD = ctypes.POINTER(ConvDesc)
 class PackItem(ctypes.Structure):
     _fields_ = [("w_oihw", ctypes.c_void_p), ("w_fprop", ctypes.c_void_p), ("w_dgrad", ctypes.c_void_p),
                 ("Cout", ctypes.c_int32), ("Cin", ctypes.c_int32), ("ksize", ctypes.c_int32), ("cout_pad", ctypes.c_int32),
-                ("cin_pad", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("cin_pad", ctypes.c_int32), ("reserved", ctypes.c_int32), ("fold_scale", ctypes.c_void_p)]
 
 
 class UnpackItem(ctypes.Structure):
@@ -32,6 +32,8 @@ SIGS = {
     "cy4_set_option": (c_i, [ctypes.c_char_p, c_i]),
     "cy4_conv_fwd": (c_i, [PD, c_f, c_f, c_f, c_f, c_f, c_f, c_vp]),
     "cy4_conv_dgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
+    "cy4_conv_fwd_fused": (c_i, [PD, c_f, c_f, c_f, c_f, c_i, c_f, c_i64, c_vp]),
+    "cy4_conv_dgrad_fused": (c_i, [PD, c_f, c_f, c_f, c_f, c_i64, c_f, c_f, c_i, c_f, c_f, c_vp]),
     "cy4_conv_wgrad": (c_i, [PD, c_f, c_f, c_f, c_vp]),
     "cy4_conv_wgrad_plan": (c_i, [PD, c_vp]),
     "cy4_pack_weight_fprop": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_vp]),

@@ -62,15 +62,37 @@ def conv_fwd(x_nhwc, w_packed, Cout, k, stride, pad, out=None, out_f32=False, bi
     return out
 
 
-def conv_dgrad(dy_nhwc, w_dgrad, Hi, Wi, Cin, k, stride, pad, out=None, accumulate=False):
-    """dy [B,Ho,Wo,Cout] fp16 -> dx [B,Hi,Wi,Cin] fp16."""
+def conv_fwd_fused(x_nhwc, w_packed, Cout, k, stride, pad, shift, act, residual=None, out=None, a_matrix=False):
+    """Eval-mode fused layer: out = act(conv(x, w_folded) + shift[c]) (+ residual), fp16 NHWC (cy4_conv_fwd_fused)."""
+    L = _lib.lib()
+    B, Hi, Wi, Cin = x_nhwc.shape
+    Ho = (Hi + 2 * pad - k) // stride + 1
+    Wo = (Wi + 2 * pad - k) // stride + 1
+    if out is None:
+        out = torch.empty(B, Ho, Wo, rup(Cout, 32), device=x_nhwc.device, dtype=torch.float16)
+    d = conv_desc(B, Hi, Wi, Cin, Cout, k, stride, pad, x_nhwc.stride(2), out.stride(2), CONV_A_MATRIX if a_matrix else 0)
+    _lib.check(L.cy4_conv_fwd_fused(ctypes.byref(d), x_nhwc.data_ptr(), w_packed.data_ptr(), out.data_ptr(), shift.data_ptr(), int(act),
+                                    residual.data_ptr() if residual is not None else None,
+                                    residual.stride(2) if residual is not None else 0, _lib.stream()), "conv_fwd_fused")
+    return out
+
+
+def conv_dgrad(dy_nhwc, w_dgrad, Hi, Wi, Cin, k, stride, pad, out=None, accumulate=False, fuse=None):
+    """dy [B,Ho,Wo,Cout] fp16 -> dx [B,Hi,Wi,Cin] fp16.
+    fuse = (y_producer [B,Hi,Wi,Cin] fp16, scale [Cin], shift [Cin], act, sum_dz [Cin], sum_dzy [Cin]): cy4_conv_dgrad_fused --
+    dx receives dz = dx_total * act'(scale*Y + shift) and the two per-channel sums are accumulated."""
     L = _lib.lib()
     B, Ho, Wo, Cout = dy_nhwc.shape
     if out is None:
         out = torch.empty(B, Hi, Wi, Cin, device=dy_nhwc.device, dtype=torch.float16)
     d = conv_desc(B, Hi, Wi, Cin, Cout, k, stride, pad, out.stride(2), dy_nhwc.stride(2), CONV_ACCUM if accumulate else 0)
     assert (d.Ho, d.Wo) == (Ho, Wo)
-    _lib.check(L.cy4_conv_dgrad(ctypes.byref(d), dy_nhwc.data_ptr(), w_dgrad.data_ptr(), out.data_ptr(), _lib.stream()), "conv_dgrad")
+    if fuse is None:
+        _lib.check(L.cy4_conv_dgrad(ctypes.byref(d), dy_nhwc.data_ptr(), w_dgrad.data_ptr(), out.data_ptr(), _lib.stream()), "conv_dgrad")
+    else:
+        yp, sc, sh, act, s1, s2 = fuse
+        _lib.check(L.cy4_conv_dgrad_fused(ctypes.byref(d), dy_nhwc.data_ptr(), w_dgrad.data_ptr(), out.data_ptr(), yp.data_ptr(), yp.stride(2),
+                                          sc.data_ptr(), sh.data_ptr(), int(act), s1.data_ptr(), s2.data_ptr(), _lib.stream()), "conv_dgrad_fused")
     return out
 
 

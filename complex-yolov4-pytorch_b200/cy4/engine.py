@@ -142,17 +142,24 @@ class StepEngine:
         if params and params[0].device != x.device:
             raise RuntimeError("Darknet parameters are on %s but the input is on %s" % (params[0].device, x.device))
         training_graph = targets is not None and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        # eval-mode forward without a backward pass: BatchNorm folded into the packed weights, activation (+ shortcut) in the
+        # conv epilogue, no raw conv outputs kept
+        infer = (not model.training) and not training_graph and bool(getattr(model, "fuse_eval", True))
         key = (tuple(x.shape), x.device, model.training, targets is not None,
-               tuple(p.data_ptr() for p in params[:4]), len(params))
+               tuple(p.data_ptr() for p in params[:4]), len(params), infer)
         with torch.cuda.device(x.device):
             if self.key != key:
-                self.plan = Plan(model, x.shape, x.device, self.L)
+                self.plan = None                          # release the old plan's buffers before allocating the new ones
+                self.plan = Plan(model, x.shape, x.device, self.L, infer=infer)
                 self.key = key
             self.plan.params = params
             if targets is None:
                 with torch.no_grad():
                     self._forward(x, None)
-                return self.plan.outputs().to("cpu")      # reference: to_cpu(torch.cat(yolo_outputs, 1))
+                out = self.plan.outputs()
+                if getattr(model, "outputs_on_device", False):
+                    return out                            # device-resident: feed utils.evaluation_utils.post_processing_v2 directly
+                return out.to("cpu")                      # reference: to_cpu(torch.cat(yolo_outputs, 1))
             if training_graph:
                 loss = _NetFn.apply(self, x, targets, *params)
             else:
@@ -220,10 +227,11 @@ class StepEngine:
 class Plan:
     """Buffers + op lists for one (batch, height, width) on one device."""
 
-    def __init__(self, model, xshape, device, L):
+    def __init__(self, model, xshape, device, L, infer=False):
         self.L = L
         self.model = model
         self.device = device
+        self.infer = infer
         self.B, cin, self.H, self.W = xshape
         assert cin == 3, "the BEV input has 3 channels"
         self.scale_target = float(model.grad_scale_target)
@@ -371,7 +379,8 @@ class Plan:
                     assert conv.in_channels * k * k <= 32, "stem conv must have C*k*k <= 32"
                     rec["cols"] = Storage(B, inf["H"], inf["W"], 32, dev, ld=32)
                 if bn is not None:
-                    rec["Y"] = Storage(B, inf["H"], inf["W"], Cout, dev)
+                    rec["Y"] = None if self.infer else Storage(B, inf["H"], inf["W"], Cout, dev)
+                    rec["M"] = B * inf["H"] * inf["W"]
                     if ind in fused_convs:                      # conv + BN + act + residual -> shortcut output
                         sc = fused_convs[ind]
                         rec["res"] = outs[info[sc]["srcs"][0]]
@@ -477,12 +486,13 @@ class Plan:
                 rec["wf"] = torch.zeros(rup(Cout, 32), 32, device=dev, dtype=torch.float16)
             else:
                 rec["wf"] = torch.empty(rup(Cout, 32), k * k * Cin, device=dev, dtype=torch.float16)
-                rec["wd"] = torch.empty(rup(Cin, 32), k * k * rup(Cout, 32), device=dev, dtype=torch.float16)
+                if not self.infer:
+                    rec["wd"] = torch.empty(rup(Cin, 32), k * k * rup(Cout, 32), device=dev, dtype=torch.float16)
             rec["wver"] = -1
-        self.acc_flat = f32(max(atot, 1))
+        self.acc_flat = f32(1 if self.infer else max(atot, 1))          # (an inference plan has no backward buffers)
         for rec in self.convs:
             n = rec["ashape"][0] * rec["ashape"][1] * rec["ashape"][2]
-            rec["acc"] = self.acc_flat[rec["aoff"]:rec["aoff"] + n].view(rec["ashape"])
+            rec["acc"] = None if self.infer else self.acc_flat[rec["aoff"]:rec["aoff"] + n].view(rec["ashape"])
         self.gw_numel = max(wtot, 1)
         self.gw_flat = None
         self._unpack_dev = None
@@ -490,7 +500,7 @@ class Plan:
         self.pool_scratch = None
         max_dy = 0
         for rec in self.convs:
-            max_dy = max(max_dy, rec["Y"].M * rup(rec["Cout"], 64) if rec["bn"] is not None else rec["P"].M * 64)
+            max_dy = max(max_dy, rec["M"] * rup(rec["Cout"], 64) if rec["bn"] is not None else rec["P"].M * 64)
         self._max_dy = max_dy
         self._storages = set()
         for rec in self.convs:
@@ -508,8 +518,19 @@ class Plan:
         from ._sigs_engine import PackItem
         L = self.L
         sig = tuple((rec["conv"].weight._version, rec["conv"].weight.data_ptr()) for rec in self.convs)
+        if self.infer:      # the folded packs also depend on the BatchNorm parameters and running statistics
+            sig += tuple(t._version for rec in self.convs if rec["bn"] is not None
+                         for t in (rec["bn"].weight, rec["bn"].bias, rec["bn"].running_mean, rec["bn"].running_var))
         if sig == getattr(self, "_pack_sig", None) and not self.force_pack:
             return
+        if self.infer:      # scale = gamma * rsqrt(running_var + eps), shift = beta - running_mean * scale  (per layer, once)
+            for rec in self.convs:
+                bn = rec["bn"]
+                if bn is None:
+                    continue
+                q = [self.bnq[i, rec["coff"]:].data_ptr() for i in range(4)]
+                self._call(L.cy4_bn_finalize, None, None, 1.0, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                           bn.running_var.data_ptr(), None, float(bn.momentum), float(bn.eps), 0, rec["Cout"], q[0], q[1], q[2], q[3], st)
         ptrs = tuple(p for _, p in sig)
         if ptrs != getattr(self, "_pack_ptrs", None):
             items = []
@@ -518,9 +539,11 @@ class Plan:
                     continue
                 it = PackItem()
                 w = rec["conv"].weight
-                it.w_oihw, it.w_fprop, it.w_dgrad = w.data_ptr(), rec["wf"].data_ptr(), rec["wd"].data_ptr()
+                it.w_oihw, it.w_fprop, it.w_dgrad = w.data_ptr(), rec["wf"].data_ptr(), (rec["wd"].data_ptr() if "wd" in rec else None)
                 it.Cout, it.Cin, it.ksize = rec["Cout"], rec["Cin"], rec["k"]
                 it.cout_pad, it.cin_pad = rup(rec["Cout"], 32), rup(rec["Cin"], 32)
+                if self.infer:
+                    it.fold_scale = self.bnq[0, rec["coff"]:].data_ptr() if rec["bn"] is not None else None
                 items.append(it)
             arr = (PackItem * len(items))(*items)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
@@ -530,8 +553,10 @@ class Plan:
         self._pack_sig = sig
         for rec in self.convs:
             if rec["stem"]:       # (r, s, c) column order of cy4_stem_im2col, padded to 32
-                w = rec["conv"].weight
-                rec["wf"][:rec["Cout"], :rec["Cin"] * rec["k"] ** 2] = w.detach().permute(0, 2, 3, 1).reshape(rec["Cout"], -1).to(torch.float16)
+                w = rec["conv"].weight.detach().permute(0, 2, 3, 1).reshape(rec["Cout"], -1)
+                if self.infer and rec["bn"] is not None:
+                    w = w * self.bnq[0, rec["coff"]:rec["coff"] + rec["Cout"], None]
+                rec["wf"][:rec["Cout"], :rec["Cin"] * rec["k"] ** 2] = w.to(torch.float16)
         if self._pack_n:
             self._call(L.cy4_pack_weights_batched, self._pack_table.data_ptr(), self._pack_n, st)
 
@@ -602,7 +627,13 @@ class Plan:
             d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, 0, 0)
             src_ptr = src.ptr
             amat = 0
-        if rec["bn"] is not None:
+        if rec["bn"] is not None and self.infer:
+            A, res = rec["A"], rec["res"]
+            d.ldy = A.ld
+            d.flags = amat
+            self._call(L.cy4_conv_fwd_fused, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), A.ptr, self.bnq[1, rec["coff"]:].data_ptr(),
+                       rec["act"], res.ptr if res is not None else None, res.ld if res is not None else 0, st)
+        elif rec["bn"] is not None:
             bn = rec["bn"]
             Y, A = rec["Y"], rec["A"]
             res = rec["res"]

@@ -47,6 +47,17 @@ def removePoints(PointCloud, BoundaryCond):
 def makeBVFeature(PointCloud_, Discretization, bc):
     """[n,4] cropped + shifted points -> float64 [3, 608, 608] (intensity, height, density), reference :39-76.
     The density channel carries float32 precision (the reference rounds it to float32 right after, kitti_dataset.py:113)."""
+    import torch.utils.data as tud
+    if tud.get_worker_info() is not None:
+        # KittiDataset.__getitem__ runs in forked DataLoader workers (train.py defaults to num_workers=4) and a forked
+        # child cannot use the parent's CUDA context.  This drop-in therefore does NOT replace the per-sample call inside
+        # workers: it hands it back to the reference's own function.  The GPU rasteriser is for main-process / batched use
+        # (num_workers=0, or cy4.bevops.rasterize(list_of_scans) on the whole batch).
+        if _ref is None:
+            raise RuntimeError("data_process.kitti_bev_utils.makeBVFeature was called inside a DataLoader worker process: the GPU "
+                               "rasteriser cannot run in a forked worker and the reference module is not importable to take the "
+                               "call -- use num_workers=0 or rasterise the batch in the main process (cy4.bevops.rasterize)")
+        return _ref.makeBVFeature(PointCloud_, Discretization, bc)
     rgb = bevops.rasterize([np.asarray(PointCloud_, np.float32)], bc, Discretization, bevops.BEV_HEIGHT, bevops.BEV_WIDTH, apply_filter=False)
     return rgb[0].cpu().numpy().astype(np.float64)
 

@@ -154,9 +154,25 @@ CY4_API int cy4_set_option(const char *name, int value);
 /* y = conv(x, w) */
 CY4_API int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias,
                          float *ch_sum, float *ch_sqsum, void *stream);
+/* Eval-mode inference: y = act(conv(x, w_folded) + shift[c]) (+ residual), fp16 NHWC.  BatchNorm
+ * (running statistics) is folded into the packed weights (cy4_pack_item.fold_scale) and `shift` = beta - mean*scale;
+ * Mish / LeakyReLU run in the conv epilogue on the fp32 accumulators; `residual` (NULL or fp16 [B*Ho*Wo, ldr]) is the
+ * shortcut input of a fused [shortcut] block.  Replaces nn.Conv2d + nn.BatchNorm2d(eval) + Mish/LeakyReLU (+ shortcut)
+ * of models/darknet2pytorch.py:247-278,208-219 as ONE kernel.  d->flags may only carry CY4_CONV_A_MATRIX. */
+CY4_API int cy4_conv_fwd_fused(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *shift, int act,
+                               const void *residual, int64_t ldr, void *stream);
 /* dx (+)= conv_transpose(dy, w); d describes the FORWARD conv; dy [B,Ho,Wo,Cout] (ld = ldy),
  * dx [B,Hi,Wi,Cin] (ld = ldx).  stride 1 (any odd k, pad = k/2) and stride 2 (k=3, pad=1, even Hi/Wi). */
 CY4_API int cy4_conv_dgrad(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, void *stream);
+/* Input gradient fused with the first pass of the PRODUCER's BatchNorm/activation backward.  dx is the gradient of the
+ * producer's activated output A = act(scale*Y + shift); instead of dA this call stores dz = dA_total * act'(scale*Y + shift)
+ * (dA_total includes the previous contents of dx when CY4_CONV_ACCUM is set -- use it on the LAST writer of that
+ * gradient) and accumulates sum_dz[c] += sum_m dz, sum_dzy[c] += sum_m dz*Y (fp32 atomics; caller zeroes them).
+ * y_producer: the producer's raw conv output, fp16 [B*Hi*Wi, ldyp]; scale/shift: its BatchNorm scale/shift [Cin].
+ * Equivalent to cy4_conv_dgrad followed by the reduce half of cy4_bn_act_bwd_reduce (sum_dzx = rstd*(sum_dzy - mean*sum_dz)). */
+CY4_API int cy4_conv_dgrad_fused(const cy4_conv_desc *d, const void *dy, const void *w_dgrad, void *dx, const void *y_producer,
+                                 int64_t ldyp, const float *scale, const float *shift, int act, float *sum_dz, float *sum_dzy,
+                                 void *stream);
 /* dw_acc[Cout_pad][kh*kw][Cin] (fp32, caller-zeroed) += dy^T * im2col(x): split-K partial sums are
  * added with atomics.  cy4_unpack_wgrad then writes the OIHW fp32 gradient of the parameter. */
 CY4_API int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void *dy, float *dw_acc, void *stream);
@@ -176,6 +192,8 @@ typedef struct cy4_pack_item {
     void *w_fprop;           /* [cout_pad][k*k][Cin] fp16, or NULL */
     void *w_dgrad;           /* [cin_pad][k*k][cout_pad] fp16, or NULL */
     int32_t Cout, Cin, ksize, cout_pad, cin_pad, reserved;
+    const float *fold_scale; /* NULL, or [Cout] fp32: w_fprop rows are multiplied by it (eval-mode BatchNorm folding,
+                                gamma * rsqrt(running_var + eps); the matching shift goes to cy4_conv_fwd_fused) */
 } cy4_pack_item;
 typedef struct cy4_unpack_item {
     const float *dw_acc;     /* [Cout_pad][k*k][Cin] fp32 */

@@ -230,6 +230,50 @@ def test_eval_mode_and_inference_api(tmp_path):
         assert torch.equal(v.cpu(), sd[k]), k          # eval must not touch running stats
 
 
+@pytest.mark.parametrize("cfgname,size,B", [("complex_yolov4_tiny", 160, 3), ("complex_yolov4", 224, 2)])
+def test_fused_inference_vs_oracle_and_unfused(cfgname, size, B):
+    """Row f2: model.eval() forward with BatchNorm folded into the weights and the activation (+ shortcut) in the conv
+    epilogue (one kernel per conv block) against (a) the fp32 oracle in eval mode and (b) the unfused engine path."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    from oracle import darknet_oracle as do
+    cfg = netdefs.cfg_path(cfgname)
+    torch.manual_seed(4)
+    model = Darknet(cfg, True)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.7, 1.3); m.bias.data.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = synth.make_bev(B, img_size=size, seed=9)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    _, oo, _ = do.forward(do.parse_cfg(cfg), sd, x, None, True, training=False)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        fused = model(x.cuda())
+        assert model._engine.plan.infer and all(r["Y"] is None for r in model._engine.plan.convs if r["bn"] is not None)
+        model.outputs_on_device = True
+        dev = model(x.cuda())
+        assert dev.is_cuda and torch.equal(dev.cpu(), fused)
+        model.outputs_on_device = False
+        model.fuse_eval = False
+        unfused = model(x.cuda())
+        assert not model._engine.plan.infer
+    rel = lambda a, b: ((a - b).abs() / (b.abs() + 1.0)).max().item()
+    print(cfgname, "fused vs oracle", rel(fused, oo), "unfused vs oracle", rel(unfused, oo), "fused vs unfused", rel(fused, unfused))
+    assert fused.shape == oo.shape and rel(fused, oo) < 2e-2 and rel(fused, unfused) < 2e-2
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    # weights changed in place: the folded packs follow (BatchNorm parameters are part of the pack signature)
+    with torch.no_grad():
+        model.fuse_eval = True
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.bias.add_(0.05)
+        moved = model(x.cuda())
+    assert rel(moved, fused) > 1e-4
+
+
 def test_elementwise_kernels_vs_torch():
     """BN finalize/apply/backward, Mish/leaky, max pool, upsample against torch on the same fp16 data."""
     import ctypes
