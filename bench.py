@@ -103,7 +103,12 @@ def run_ours(args):
     net.use_cuda_graph = bool(args.cuda_graph)
     model = net
     if world > 1:
+        # unchanged PyTorch DDP (parameter broadcast, bucket views); the gradient all-reduce itself is issued by the engine in
+        # groups while backward is still running (models/model_utils.py overlap_gradient_exchange), unless --ddp-stock
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=128)
+        if not args.ddp_stock:
+            from models.model_utils import overlap_gradient_exchange
+            overlap_gradient_exchange(model)
     opt = make_optimizer(net)
     x_host = synth.make_bev(B, seed=1234 + rank).pin_memory()
     tg_host = torch.tensor(synth.make_targets(B, per_image=5, seed=4321 + rank)).pin_memory()
@@ -160,9 +165,16 @@ def run_ours(args):
             ev.record(copy_stream)
         return xd_, td_, ev
 
+    # Every step: H2D of its own batch from pinned memory (issued one step ahead on a copy stream), D2H of the step's loss
+    # and detections into pinned memory.  The host reads step i's loss while step i+1 is already enqueued (a training loop
+    # that logs the previous step's loss), so the ~850 kernel launches of a step are issued ahead of the GPU instead of
+    # after a per-step host synchronisation; the last step's results are read inside the timed region.
+    loss_host = torch.zeros(2, 1, pin_memory=True)
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     sync()
     t0 = time.perf_counter()
     nxt = h2d()
+    lval = None
     for i in range(args.steps):
         xd, td, ev = nxt
         torch.cuda.current_stream().wait_event(ev)
@@ -173,7 +185,13 @@ def run_ours(args):
             nxt = h2d()                      # every step copies its own batch from the host, one step ahead
         opt.step()
         opt.zero_grad(set_to_none=True)
-        lval = float(loss.item())            # device -> host read of the step's result (and `out` is on the CPU)
+        loss_host[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)     # device -> host read of the step's result
+        loss_ev[i & 1].record()
+        if i > 0:
+            loss_ev[(i - 1) & 1].synchronize()
+            lval = float(loss_host[(i - 1) & 1])
+    loss_ev[(args.steps - 1) & 1].synchronize()
+    lval = float(loss_host[(args.steps - 1) & 1])
     sync()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -516,6 +534,8 @@ def main():
     ap.add_argument("--cuda-graph", dest="cuda_graph", type=int, default=0, help="replay the fwd/bwd launch sequences as CUDA graphs")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT",
                     help="cy4_set_option(NAME, INT) before the run (kernel experiments, e.g. conv_cluster=2); recorded in config")
+    ap.add_argument("--ddp-stock", dest="ddp_stock", action="store_true",
+                    help="N>1: let stock DDP do the (un-overlapped) bucketed all-reduce instead of the engine's overlapped exchange")
     ap.add_argument("--no-roofline", dest="no_roofline", action="store_true", help="skip the per-launch roofline pass (quick A/B runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

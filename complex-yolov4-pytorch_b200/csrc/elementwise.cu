@@ -189,6 +189,14 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, __half *__re
     }
 }
 
+// raw sums of a fused dgrad epilogue (sum dz, sum dz*y) -> sum dz*xhat = rstd * (sum dz*y - mean * sum dz), in place
+__global__ void bn_bwd_fixup_kernel(const float *__restrict__ sum_dz, float *__restrict__ sum_dzy, const float *__restrict__ mean,
+                                    const float *__restrict__ rstd, int C)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) sum_dzy[c] = rstd[c] * (sum_dzy[c] - mean[c] * sum_dz[c]);
+}
+
 // dY = scale * (dz - sum_dz/M - xhat * sum_dzx/M)   (training-mode BN backward; eval: dY = scale*dz)
 //    = scale * dz + A * y + B   with  A = -scale*rstd*sum_dzx/M,  B = -scale*sum_dz/M - A*mean
 // DZ_READY: the reduce pass already replaced dA by dz, so this pass is three FMAs per element.
@@ -508,6 +516,13 @@ int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, con
     if (act == ACT_MISH) CY4_RED(ACT_MISH); else if (act == ACT_LEAKY) CY4_RED(ACT_LEAKY); else CY4_RED(ACT_LINEAR);
 #undef CY4_RED
     return cy4_launch_status("cy4_bn_act_bwd_reduce");
+}
+
+int cy4_bn_bwd_fixup(const float *sum_dz, float *sum_dzy_inout, const float *mean, const float *rstd, int C, void *stream)
+{
+    CY4_CHECK_ARG(sum_dz && sum_dzy_inout && mean && rstd && C > 0, "cy4_bn_bwd_fixup: bad argument");
+    bn_bwd_fixup_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum_dz, sum_dzy_inout, mean, rstd, C);
+    return cy4_launch_status("cy4_bn_bwd_fixup");
 }
 
 int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,

@@ -47,6 +47,7 @@ SIGS = {
                                 c_f, c_f, c_f, c_f, c_vp]),
     "cy4_bn_act_fwd": (c_i, [c_f, c_i64, c_f, c_f, c_i, c_f, c_i64, c_f, c_i64, c_i64, c_i, c_vp]),
     "cy4_bn_act_bwd_reduce": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_f, c_f, c_f, c_i, c_i64, c_i, c_f, c_f, c_vp]),
+    "cy4_bn_bwd_fixup": (c_i, [c_f, c_f, c_f, c_f, c_i, c_vp]),
     "cy4_bn_act_bwd_apply": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_f, c_f, c_f, c_f, c_f, ctypes.c_float, c_i, c_i, c_i, c_f, c_i64,
                                      c_i64, c_i, c_vp]),
     "cy4_add_copy": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_i64, c_i64, c_i, c_vp]),

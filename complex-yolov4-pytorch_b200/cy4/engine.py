@@ -146,7 +146,7 @@ class StepEngine:
         # conv epilogue, no raw conv outputs kept
         infer = (not model.training) and not training_graph and bool(getattr(model, "fuse_eval", True))
         key = (tuple(x.shape), x.device, model.training, targets is not None,
-               tuple(p.data_ptr() for p in params[:4]), len(params), infer)
+               tuple(p.data_ptr() for p in params[:4]), len(params), infer, bool(getattr(model, "fuse_bn_backward", True)))
         with torch.cuda.device(x.device):
             if self.key != key:
                 self.plan = None                          # release the old plan's buffers before allocating the new ones
@@ -502,6 +502,7 @@ class Plan:
         for rec in self.convs:
             max_dy = max(max_dy, rec["M"] * rup(rec["Cout"], 64) if rec["bn"] is not None else rec["P"].M * 64)
         self._max_dy = max_dy
+        self._plan_bwd_fusion()
         self._storages = set()
         for rec in self.convs:
             if "A" in rec:
@@ -511,6 +512,63 @@ class Plan:
                 self._storages.add(r[1].st)
         for st in cat_storage.values():
             self._storages.add(st)
+
+    def _plan_bwd_fusion(self):
+        """Static pass over the backward order: for every BatchNorm conv P whose activated output A receives its LAST
+        gradient contribution from the input-gradient kernel of a conv C reading exactly that view, C's epilogue takes over
+        the first pass of P's BN/activation backward (cy4_conv_dgrad_fused: dz = dA_total * act'(z) stored instead of dA,
+        sum dz / sum dz*Y accumulated) and P skips cy4_bn_act_bwd_reduce.  Tensors whose gradient is completed by a route
+        copy, a shortcut, a pooling / upsampling backward or by the consumer of a concat buffer keep the separate pass."""
+        for rec in self.convs:
+            rec["fuse_bwd"] = None          # consumer side: the producer rec whose reduce pass this conv's dgrad performs
+            rec["reduce_fused"] = False     # producer side
+        if self.infer or not bool(getattr(self.model, "fuse_bn_backward", True)):
+            return
+        writers = {}                        # id(storage) -> [(lo, hi, kind, rec)] in backward order
+        events = {}
+        for rec in self.convs:
+            events[rec["ind"]] = ("conv", rec)
+        for r in self.routes:
+            events[r[0]] = ("route", r)
+        for r in self.shorts:
+            events[r[0]] = ("short", r)
+        for r in self.pools:
+            events[r[0]] = ("pool", r)
+        for r in self.ups:
+            events[r[0]] = ("up", r)
+
+        def note(view, kind, rec=None):
+            writers.setdefault(id(view.st), []).append((view.off, view.off + view.C, kind, rec))
+
+        for ind in sorted(events, reverse=True):
+            kind, r = events[ind]
+            if kind == "conv":
+                if not r["stem"]:
+                    note(r["src"], "conv", r)
+            elif kind == "route":
+                for s_, _off in r[2]:
+                    note(s_, "copy")
+            elif kind == "short":
+                note(r[2], "copy")
+                if r[3] is not None:
+                    note(r[3], "copy")
+            elif kind == "pool":
+                note(r[2], "copy")
+            elif kind == "up":
+                note(r[2], "copy")
+        for P in self.convs:
+            if P["bn"] is None:
+                continue
+            A = P["A"]
+            lo, hi = A.off, A.off + A.C
+            ws = [w for w in writers.get(id(A.st), []) if w[0] < hi and lo < w[1]]
+            if not ws or any((w[0], w[1]) != (lo, hi) for w in ws):
+                continue                    # no gradient, or partially overlapping writers (concat consumers, channel slices)
+            last = ws[-1]
+            if last[2] != "conv" or last[3]["fuse_bwd"] is not None:
+                continue
+            last[3]["fuse_bwd"] = P
+            P["reduce_fused"] = True
 
     # ---- forward -----------------------------------------------------------------------------
     def _pack_weights(self, st):
@@ -725,10 +783,22 @@ class Plan:
             else:
                 self._call(L.cy4_add_copy, src_ptr, src_ld, None, 0, view.gptr, view.ld, M, view.C, st)
 
+        # gradient exchange done by the engine itself (model.engine_allreduce, set by models.model_utils.make_data_parallel
+        # together with a no-op DDP communication hook): grouped, asynchronous, overlapped with the rest of backward
+        ar_groups, works = None, []
+        if getattr(model, "engine_allreduce", False) and self.graph_state is None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                ar_groups = self._allreduce_groups()
+
         for ind in sorted(events, reverse=True):
             kind, r = events[ind]
             if kind == "conv":
                 self._conv_backward(r, training, st, gw_flat, grads)
+                if ar_groups is not None and ind in ar_groups:
+                    first, n, lo, hi = ar_groups[ind]
+                    self._unpack_range(st, first, n)
+                    works.append(dist.all_reduce(gw_flat[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
             elif kind == "route":
                 _, cat, copies = r
                 for s_, off in copies:                   # sources that were copied (not produced in place)
@@ -761,18 +831,60 @@ class Plan:
                 acc = src.grad_mode()
                 self._call(L.cy4_upsample2x_bwd, out.gptr, out.ld, src.gptr, src.ld, B, Hi, Wi, src.C, acc, st)
 
-        self._unpack_all(st)
+        if ar_groups is None:
+            _t, n_items = self._unpack_all(st)
+            self._unpack_range(st, 0, n_items)
+        # BN parameter gradients: d beta = sum dz, d gamma = sum dz*xhat (both carry the loss scale)
+        gbn = self.dbn * self.gscale[1]
+        if ar_groups is not None:
+            works.append(dist.all_reduce(gbn, op=dist.ReduceOp.AVG, async_op=True))
+            for rec in self.convs:
+                gb = grads.get(id(rec["conv"].bias)) if rec["conv"].bias is not None else None
+                if gb is not None:
+                    works.append(dist.all_reduce(gb, op=dist.ReduceOp.AVG, async_op=True))
+            for w_ in works:
+                w_.wait()                                # the current stream waits for the exchange; the host does not block
         fresh = gw_flat.clone()
         for w, off in self._wslices:
             grads[id(w)] = fresh[off:off + w.numel()].view_as(w)
-        # BN parameter gradients: d beta = sum dz, d gamma = sum dz*xhat (both carry the loss scale)
-        gbn = self.dbn * self.gscale[1]
         for rec in self.convs:
             if rec["bn"] is not None and rec.get("bn_bwd_done"):
                 c0, C = rec["coff"], rec["Cout"]
                 grads[id(rec["bn"].bias)] = gbn[0, c0:c0 + C]
                 grads[id(rec["bn"].weight)] = gbn[1, c0:c0 + C]
         return [grads.get(id(p)) if p.requires_grad else None for p in self.params]
+
+    def _allreduce_groups(self):
+        """Gradient exchange plan: conv layers in backward order, cut into groups of roughly equal parameter
+        bytes.  As soon as the weight gradients of a group are complete they are unpacked into their (contiguous) range of
+        the flat OIHW buffer and averaged over the ranks with an asynchronous NCCL all-reduce that overlaps the rest of the
+        backward pass -- the heavy parameters (1024-channel 3x3 layers) come first in backward, the large-activation
+        layers that hide the exchange come last."""
+        if getattr(self, "_ar_groups", None) is None:
+            convs = [r for r in self.convs if not r["stem"]]
+            total = sum(r["conv"].weight.numel() for r in convs)
+            ngroups = max(1, int(getattr(self.model, "allreduce_groups", 6)))
+            groups, cur, acc = [], [], 0
+            for item, r in reversed(list(enumerate(convs))):
+                cur.append((item, r))
+                acc += r["conv"].weight.numel()
+                if acc >= total / ngroups and len(groups) < ngroups - 1:
+                    groups.append(cur); cur, acc = [], 0
+            if cur:
+                groups.append(cur)
+            out = {}
+            for g in groups:
+                items = [i for i, _ in g]
+                lo_rec, hi_rec = g[-1][1], g[0][1]              # lowest / highest layer index of the group
+                flat_lo = lo_rec["woff"]
+                flat_hi = hi_rec["woff"] + hi_rec["conv"].weight.numel()
+                out[lo_rec["ind"]] = (min(items), len(items), flat_lo, flat_hi)
+            if self.convs and self.convs[0]["stem"]:            # the stem's gradient is written by torch ops at the very end
+                first = min(out)
+                it, n, lo, hi = out.pop(first)
+                out[self.convs[0]["ind"]] = (it, n, self.convs[0]["woff"], hi)
+            self._ar_groups = out                                 # trigger layer index -> (first item, n items, flat range)
+        return self._ar_groups
 
     def _unpack_all(self, st):
         """[Cout][tap][Cin] fp32 accumulators -> OIHW gradients of every conv, one launch.  The item
@@ -793,8 +905,15 @@ class Plan:
             if items:
                 arr = (UnpackItem * len(items))(*items)
                 self._unpack_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(self.device)
-        if self._unpack_n:
-            self._call(self.L.cy4_unpack_wgrad_batched, self._unpack_dev.data_ptr(), self._unpack_n, self.gscale[1:2].data_ptr(), st)
+        return self._unpack_dev, self._unpack_n
+
+    def _unpack_range(self, st, first, n):
+        """One launch for items [first, first+n) of the unpack table."""
+        from ._sigs_engine import UnpackItem
+        table, total = self._unpack_all(st)
+        if n > 0 and table is not None:
+            self._call(self.L.cy4_unpack_wgrad_batched, table.data_ptr() + first * ctypes.sizeof(UnpackItem), n,
+                       self.gscale[1:2].data_ptr(), st)
 
     def _conv_backward(self, rec, training, st, gw_flat, grads):
         L = self.L
@@ -812,8 +931,13 @@ class Plan:
             c0 = rec["coff"]
             q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
             sdz, sdzx = self.dbn[0, c0:].data_ptr(), self.dbn[1, c0:].data_ptr()
-            self._call(L.cy4_bn_act_bwd_reduce, Y.buf.data_ptr(), Y.ld, A.gptr, A.ld, q[0], q[1], q[2], q[3], rec["act"],
-                       Y.M, Cout, sdz, sdzx, st)
+            if rec["reduce_fused"] and rec.pop("_dz_ready", False):
+                # the last writer of A's gradient (a consumer's cy4_conv_dgrad_fused) left dz in place of dA and the raw
+                # sums (sum dz, sum dz*Y): only the per-channel conversion to sum dz*xhat is left
+                self._call(L.cy4_bn_bwd_fixup, sdz, sdzx, q[2], q[3], Cout, st)
+            else:
+                self._call(L.cy4_bn_act_bwd_reduce, Y.buf.data_ptr(), Y.ld, A.gptr, A.ld, q[0], q[1], q[2], q[3], rec["act"],
+                           Y.M, Cout, sdz, sdzx, st)
             ldy, M = rup(Cout, 64), Y.M                    # the dY scratch keeps 64-channel rows (weight-gradient TMA boxes)
             self._call(L.cy4_bn_act_bwd_apply, Y.buf.data_ptr(), Y.ld, A.gptr, A.ld, q[0], q[1], q[2], q[3], sdz, sdzx,
                        1.0 / Y.M, 1 if training else 0, rec["act"], 1, dy.data_ptr(), ldy, Y.M, Cout, st)
@@ -838,7 +962,15 @@ class Plan:
             src = rec["src"]
             acc = src.grad_mode()
             d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, cpad, k, stride, pad, src.ld, ldy, co.CONV_ACCUM if acc else 0)
-            self._call(L.cy4_conv_dgrad, ctypes.byref(d), dy.data_ptr(), rec["wd"].data_ptr(), src.gptr, st)
+            P = rec["fuse_bwd"]
+            if P is not None:
+                pc = P["coff"]
+                self._call(L.cy4_conv_dgrad_fused, ctypes.byref(d), dy.data_ptr(), rec["wd"].data_ptr(), src.gptr, P["Y"].buf.data_ptr(),
+                           P["Y"].ld, self.bnq[0, pc:].data_ptr(), self.bnq[1, pc:].data_ptr(), P["act"],
+                           self.dbn[0, pc:].data_ptr(), self.dbn[1, pc:].data_ptr(), st)
+                P["_dz_ready"] = True
+            else:
+                self._call(L.cy4_conv_dgrad, ctypes.byref(d), dy.data_ptr(), rec["wd"].data_ptr(), src.gptr, st)
         # weight gradient (accumulator zeroed once per backward with the flat buffer)
         gw = gw_flat[rec["woff"]:rec["woff"] + conv.weight.numel()].view_as(conv.weight)
         if rec["stem"]:

@@ -21,6 +21,17 @@ def get_num_parameters(model):
     return sum(p.numel() for p in m.parameters() if p.requires_grad)
 
 
+def overlap_gradient_exchange(ddp_model):
+    """The B200 engine exposes the whole network as one autograd node, so stock DDP would start its bucketed all-reduce only
+    after the last backward kernel.  Instead the engine averages the gradients itself while backward is still running
+    (cy4/engine.py: grouped asynchronous NCCL all-reduce, heavy layers first) and DDP keeps everything else it does
+    (parameter broadcast at construction, bucket views, no_sync bookkeeping) with a no-op communication hook."""
+    from torch.distributed.algorithms.ddp_comm_hooks.debugging_hooks import noop_hook
+    ddp_model.module.engine_allreduce = True
+    ddp_model.register_comm_hook(None, noop_hook)
+    return ddp_model
+
+
 def make_data_parallel(model, configs):
     """Reference :41-67: DistributedDataParallel (one process per GPU), single GPU, or DataParallel."""
     if configs.distributed:
@@ -29,10 +40,10 @@ def make_data_parallel(model, configs):
             model.cuda(configs.gpu_idx)
             configs.batch_size = int(configs.batch_size / configs.ngpus_per_node)
             configs.num_workers = int((configs.num_workers + configs.ngpus_per_node - 1) / configs.ngpus_per_node)
-            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[configs.gpu_idx])
+            model = overlap_gradient_exchange(torch.nn.parallel.DistributedDataParallel(model, device_ids=[configs.gpu_idx]))
         else:
             model.cuda()
-            model = torch.nn.parallel.DistributedDataParallel(model)
+            model = overlap_gradient_exchange(torch.nn.parallel.DistributedDataParallel(model))
     elif configs.gpu_idx is not None:
         torch.cuda.set_device(configs.gpu_idx)
         model = model.cuda(configs.gpu_idx)

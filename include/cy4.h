@@ -227,6 +227,9 @@ CY4_API int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const
 CY4_API int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, const float *scale, const float *shift,
                                   const float *mean, const float *rstd, int act, int64_t M, int C, float *sum_dz, float *sum_dzx,
                                   void *stream);
+/* After cy4_conv_dgrad_fused: converts its raw per-channel sums in place, sum_dzy <- rstd * (sum_dzy - mean * sum_dz)
+ * (= sum dz*xhat = d gamma), which is what cy4_bn_act_bwd_reduce would have produced. */
+CY4_API int cy4_bn_bwd_fixup(const float *sum_dz, float *sum_dzy_inout, const float *mean, const float *rstd, int C, void *stream);
 /* dY = scale*(dz - sum_dz/M - xhat*sum_dzx/M) (training) or scale*dz (eval).  dz_ready != 0: dA already
  * holds dz (cy4_bn_act_bwd_reduce ran on it); otherwise dz = dA*act'(z) is recomputed here. */
 CY4_API int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg, const float *scale, const float *shift,

@@ -274,6 +274,39 @@ def test_fused_inference_vs_oracle_and_unfused(cfgname, size, B):
     assert rel(moved, fused) > 1e-4
 
 
+@pytest.mark.parametrize("cfgname,size,B", [("complex_yolov4_tiny", 256, 2), ("complex_yolov4", 224, 2)])
+def test_fused_bn_backward_matches_separate_pass(cfgname, size, B):
+    """cy4_conv_dgrad_fused (the first BN/activation-backward pass inside the input-gradient epilogue of the tensor's last
+    gradient writer) against the separate cy4_bn_act_bwd_reduce pass: same step, same weights, both engine configurations.
+    The fused form computes dz from the fp32 accumulator instead of the fp16-rounded dA, so the two agree to fp16 rounding."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    strides = (16, 32) if "tiny" in cfgname else (8, 16, 32)
+    x = synth.make_bev(B, img_size=size, seed=5).cuda()
+    tg = torch.tensor(synth.make_targets(B, per_image=3, seed=2, img_size=size, strides=strides)).cuda()
+    grads, losses, nf = [], [], []
+    for fuse in (True, False):
+        torch.manual_seed(1)
+        model = Darknet(netdefs.cfg_path(cfgname), True).cuda().train()
+        model.fuse_bn_backward = fuse
+        loss, _ = model(x, tg)
+        loss.backward()
+        torch.cuda.synchronize()
+        nf.append(sum(1 for r in model._engine.plan.convs if r["reduce_fused"]))
+        losses.append(loss.item())
+        grads.append({n: p.grad.clone() for n, p in model.named_parameters()})
+    print(cfgname, "fused BN-backward layers:", nf)
+    assert nf[1] == 0 and nf[0] >= (5 if "tiny" in cfgname else 60)
+    assert abs(losses[0] - losses[1]) <= 1e-3 * abs(losses[1])       # forward is identical up to the BN-statistics atomics
+    worst = 1.0
+    for n in grads[0]:
+        c = _cos(grads[0][n], grads[1][n])
+        worst = min(worst, c)
+        nr = abs(grads[0][n].norm().item() - grads[1][n].norm().item()) / (grads[1][n].norm().item() + 1e-12)
+        assert c > 0.995 and nr < 0.02, (n, c, nr)
+    print("worst cosine fused vs separate", worst)
+
+
 def test_elementwise_kernels_vs_torch():
     """BN finalize/apply/backward, Mish/leaky, max pool, upsample against torch on the same fp16 data."""
     import ctypes
