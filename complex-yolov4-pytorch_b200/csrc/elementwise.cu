@@ -78,11 +78,21 @@ __device__ __forceinline__ RowChunk block_rows(int64_t M, int rpi)
     return r;
 }
 
+// Training-mode statistics -> scale / shift inside the apply pass (saves the separate cy4_bn_finalize launch per layer).
+struct BnFin {
+    const float *ch_sum, *ch_sqsum, *gamma, *beta;
+    float *running_mean, *running_var; long long *num_batches;
+    float *scale_out, *shift_out, *mean_out, *rstd_out;
+    float count, momentum, eps;
+};
+
 // out = act(y * scale + shift) (+ residual)
-template <int ACT, bool RES>
+// FIN: scale / shift are derived here from the batch sums (every thread for its own 8 channels); block 0 also publishes
+// scale / shift / mean / rstd for the backward pass and updates the running statistics exactly like nn.BatchNorm2d.
+template <int ACT, bool RES, bool FIN>
 __global__ void __launch_bounds__(256, 3)
 bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__restrict__ scale, const float *__restrict__ shift,
-                  const __half *__restrict__ res, int64_t ldr, __half *__restrict__ out, int64_t ldo, int64_t M, int C)
+                  const __half *__restrict__ res, int64_t ldr, __half *__restrict__ out, int64_t ldo, int64_t M, int C, const BnFin fin)
 {
     const int vpr = C >> 3;
     for (int v0 = 0; v0 < vpr; v0 += 256) {
@@ -92,8 +102,30 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
         if (rsub >= rpi) continue;
         const int c0 = (v0 + vec) << 3;
         float sc[8], sh[8];
+        if (FIN) {
+            const bool publish = blockIdx.x == 0 && rsub == 0;
+            if (publish && c0 == 0 && fin.num_batches) *fin.num_batches += 1;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+            for (int k = 0; k < 8; ++k) {
+                const int c = c0 + k;
+                const double m = (double)fin.ch_sum[c] / fin.count;
+                double v = (double)fin.ch_sqsum[c] / fin.count - m * m;
+                if (v < 0.0) v = 0.0;
+                const float mean = (float)m, var = (float)v;
+                const float rstd = rsqrtf(var + fin.eps);
+                sc[k] = fin.gamma[c] * rstd;
+                sh[k] = fin.beta[c] - mean * sc[k];
+                if (publish) {
+                    const float unbiased = fin.count > 1.f ? (float)(v * (double)fin.count / ((double)fin.count - 1.0)) : var;
+                    fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mean;
+                    fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * unbiased;
+                    fin.scale_out[c] = sc[k]; fin.shift_out[c] = sh[k]; fin.mean_out[c] = mean; fin.rstd_out[c] = rstd;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+        }
         const RowChunk rc = block_rows(M, rpi);
         for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
             uint4 vy[kUnroll], vr[kUnroll];
@@ -489,19 +521,51 @@ int cy4_bn_finalize(const float *ch_sum, const float *ch_sqsum, float count, con
     return cy4_launch_status("cy4_bn_finalize");
 }
 
+static int bn_act_fwd_launch(const void *y, int64_t ldy, const float *scale, const float *shift, int act, const void *residual, int64_t ldr,
+                             void *out, int64_t ldo, int64_t M, int C, const BnFin *fin, void *stream)
+{
+    BnFin f;
+    memset(&f, 0, sizeof(f));
+    if (fin) f = *fin;
+#define CY4_FWD(ACT, RES, FIN)                                                                                              \
+    bn_act_fwd_kernel<ACT, RES, FIN><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, \
+                                                                                       (const __half *)residual, ldr, (__half *)out, ldo, M, C, f)
+#define CY4_FWD_A(RES, FIN)                                                                     \
+    do {                                                                                        \
+        if (act == ACT_MISH) CY4_FWD(ACT_MISH, RES, FIN);                                       \
+        else if (act == ACT_LEAKY) CY4_FWD(ACT_LEAKY, RES, FIN);                                \
+        else CY4_FWD(ACT_LINEAR, RES, FIN);                                                     \
+    } while (0)
+    if (fin) { if (residual) CY4_FWD_A(true, true); else CY4_FWD_A(false, true); }
+    else { if (residual) CY4_FWD_A(true, false); else CY4_FWD_A(false, false); }
+#undef CY4_FWD_A
+#undef CY4_FWD
+    return cy4_launch_status("cy4_bn_act_fwd");
+}
+
 int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *shift, int act, const void *residual, int64_t ldr,
                    void *out, int64_t ldo, int64_t M, int C, void *stream)
 {
     EW_CHECK_C(C, "cy4_bn_act_fwd");
     CY4_CHECK_ARG(y && scale && shift && out && M >= 0 && (ldy % 8) == 0 && (ldo % 8) == 0 && (ldr % 8) == 0, "cy4_bn_act_fwd: bad argument");
     if (M == 0) return 0;
-#define CY4_FWD(ACT, RES)                                                                                                   \
-    bn_act_fwd_kernel<ACT, RES><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift,      \
-                                                                                  (const __half *)residual, ldr, (__half *)out, ldo, M, C)
-    if (residual) { if (act == ACT_MISH) CY4_FWD(ACT_MISH, true); else if (act == ACT_LEAKY) CY4_FWD(ACT_LEAKY, true); else CY4_FWD(ACT_LINEAR, true); }
-    else { if (act == ACT_MISH) CY4_FWD(ACT_MISH, false); else if (act == ACT_LEAKY) CY4_FWD(ACT_LEAKY, false); else CY4_FWD(ACT_LINEAR, false); }
-#undef CY4_FWD
-    return cy4_launch_status("cy4_bn_act_fwd");
+    return bn_act_fwd_launch(y, ldy, scale, shift, act, residual, ldr, out, ldo, M, C, nullptr, stream);
+}
+
+int cy4_bn_train_act_fwd(const void *y, int64_t ldy, const float *ch_sum, const float *ch_sqsum, float count, const float *gamma,
+                         const float *beta, float *running_mean, float *running_var, int64_t *num_batches_tracked, float momentum,
+                         float eps, float *scale, float *shift, float *mean, float *rstd, int act, const void *residual, int64_t ldr,
+                         void *out, int64_t ldo, int64_t M, int C, void *stream)
+{
+    EW_CHECK_C(C, "cy4_bn_train_act_fwd");
+    CY4_CHECK_ARG(y && ch_sum && ch_sqsum && gamma && beta && running_mean && running_var && scale && shift && mean && rstd && out &&
+                  count > 0 && M > 0 && (ldy % 8) == 0 && (ldo % 8) == 0 && (ldr % 8) == 0, "cy4_bn_train_act_fwd: bad argument");
+    BnFin f;
+    f.ch_sum = ch_sum; f.ch_sqsum = ch_sqsum; f.gamma = gamma; f.beta = beta;
+    f.running_mean = running_mean; f.running_var = running_var; f.num_batches = (long long *)num_batches_tracked;
+    f.scale_out = scale; f.shift_out = shift; f.mean_out = mean; f.rstd_out = rstd;
+    f.count = count; f.momentum = momentum; f.eps = eps;
+    return bn_act_fwd_launch(y, ldy, nullptr, nullptr, act, residual, ldr, out, ldo, M, C, &f, stream);
 }
 
 int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, const float *scale, const float *shift,

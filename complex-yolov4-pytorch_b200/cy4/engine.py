@@ -171,8 +171,22 @@ class StepEngine:
             else:
                 # asynchronous copy into pinned memory: complete at the next stream sync
                 # (train.py reads loss.item() every step, which is such a sync)
+                # The 29 MB detection tensor goes to pinned memory on a side stream, overlapped with the backward pass; the
+                # compute stream waits for that copy at the end of backward (or at the start of the next forward), so the
+                # host sees it complete at train.py's per-step loss read like before.
                 out_cpu = self.plan.pinned_out(out)
-                out_cpu.copy_(out, non_blocking=True)
+                plan = self.plan
+                if plan.d2h_stream is None:
+                    plan.d2h_stream = torch.cuda.Stream(device=x.device)
+                    plan.d2h_done = torch.cuda.Event()
+                ready = torch.cuda.Event()
+                ready.record()
+                with torch.cuda.stream(plan.d2h_stream):
+                    plan.d2h_stream.wait_event(ready)
+                    out_cpu.copy_(out, non_blocking=True)
+                    plan.d2h_done.record()
+                out.record_stream(plan.d2h_stream)
+                plan.d2h_pending = True
             return loss, out_cpu
 
     # ---- optional CUDA-graph replay of the two launch sequences (model.use_cuda_graph) --------------
@@ -241,6 +255,7 @@ class Plan:
         self.prof = None             # list -> CUDA-event timing of every conv launch (bench.py roofline pass)
         self.graph_state = None
         self.force_pack = False
+        self.d2h_stream, self.d2h_done, self.d2h_pending = None, None, False
         self._build()
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -623,6 +638,7 @@ class Plan:
         st = _lib.stream()
         model = self.model
         training = model.training
+        self.join_d2h()                    # the previous step's detections leave the pinned buffer intact until copied
         x = x.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
@@ -701,11 +717,17 @@ class Plan:
             s1 = self.stats[0, c0:].data_ptr(); s2 = self.stats[1, c0:].data_ptr()
             self._call(L.cy4_conv_fwd, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), Y.buf.data_ptr(), None, s1, s2, st)
             q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
-            self._call(L.cy4_bn_finalize, s1, s2, float(Y.M), bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
-                       bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), float(bn.momentum), float(bn.eps),
-                       1 if training else 0, Cout, q[0], q[1], q[2], q[3], st)
-            self._call(L.cy4_bn_act_fwd, Y.buf.data_ptr(), Y.ld, q[0], q[1], rec["act"], res.ptr if res is not None else None,
-                       res.ld if res is not None else 0, A.ptr, A.ld, Y.M, Cout, st)
+            if training:      # batch statistics -> scale / shift inside the apply pass (one launch)
+                self._call(L.cy4_bn_train_act_fwd, Y.buf.data_ptr(), Y.ld, s1, s2, float(Y.M), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                           bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), float(bn.momentum),
+                           float(bn.eps), q[0], q[1], q[2], q[3], rec["act"], res.ptr if res is not None else None,
+                           res.ld if res is not None else 0, A.ptr, A.ld, Y.M, Cout, st)
+            else:
+                self._call(L.cy4_bn_finalize, s1, s2, float(Y.M), bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                           bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), float(bn.momentum), float(bn.eps),
+                           0, Cout, q[0], q[1], q[2], q[3], st)
+                self._call(L.cy4_bn_act_fwd, Y.buf.data_ptr(), Y.ld, q[0], q[1], rec["act"], res.ptr if res is not None else None,
+                           res.ld if res is not None else 0, A.ptr, A.ld, Y.M, Cout, st)
         else:
             P = rec["P"]
             d.ldy = P.ld
@@ -717,6 +739,12 @@ class Plan:
                 rec["bias32"][:Cout] = bias.detach()
             self._call(L.cy4_conv_fwd, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), P.buf.data_ptr(),
                        rec["bias32"].data_ptr() if bias is not None else None, None, None, st)
+
+    def join_d2h(self):
+        """Make the compute stream wait for the asynchronous detections copy of this plan (if one is in flight)."""
+        if self.d2h_pending:
+            torch.cuda.current_stream().wait_event(self.d2h_done)
+            self.d2h_pending = False
 
     def outputs(self):
         return torch.cat([y["out"] for y in self.yolos], 1)
@@ -844,6 +872,7 @@ class Plan:
                     works.append(dist.all_reduce(gb, op=dist.ReduceOp.AVG, async_op=True))
             for w_ in works:
                 w_.wait()                                # the current stream waits for the exchange; the host does not block
+        self.join_d2h()
         fresh = gw_flat.clone()
         for w, off in self._wslices:
             grads[id(w)] = fresh[off:off + w.numel()].view_as(w)

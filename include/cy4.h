@@ -219,6 +219,13 @@ CY4_API int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int
 CY4_API int cy4_bn_finalize(const float *ch_sum, const float *ch_sqsum, float count, const float *gamma, const float *beta,
                             float *running_mean, float *running_var, int64_t *num_batches_tracked, float momentum, float eps,
                             int training, int C, float *scale, float *shift, float *mean, float *rstd, void *stream);
+/* cy4_bn_finalize(training=1) + cy4_bn_act_fwd in ONE launch: every thread derives scale / shift of its channels from the
+ * batch sums; scale / shift / mean / rstd (for the backward pass), running_mean / running_var / num_batches_tracked are
+ * written once, with nn.BatchNorm2d's update rule (darknet2pytorch.py:260, momentum, unbiased variance). */
+CY4_API int cy4_bn_train_act_fwd(const void *y, int64_t ldy, const float *ch_sum, const float *ch_sqsum, float count, const float *gamma,
+                                 const float *beta, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                                 float momentum, float eps, float *scale, float *shift, float *mean, float *rstd, int act,
+                                 const void *residual, int64_t ldr, void *out, int64_t ldo, int64_t M, int C, void *stream);
 /* out = act(y*scale + shift) (+ residual) */
 CY4_API int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *shift, int act, const void *residual,
                            int64_t ldr, void *out, int64_t ldo, int64_t M, int C, void *stream);
