@@ -26,6 +26,7 @@ int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disable
 int g_conv_pair = 0;        // 1: experimental CTA-pair (cta_group::2) conv kernel for the eligible launches (conv_pair.cu), not yet measured
 int g_wgrad_variant = 1;    // 2: experimental persistent kernel (conv_wgrad2.cu), not yet measured
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
+int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
 struct GenericConv {
@@ -169,50 +170,77 @@ __global__ void unpack_wgrad_kernel(const float *__restrict__ acc, int Cout, int
 }
 
 // ---- batched variants: one launch for every conv layer of the network ------------------------------
-__global__ void pack_batched_kernel(const cy4_pack_item *__restrict__ items)
+// Both directions are (co, ci, tap) <-> (co, tap, ci) / (ci, tap, co) re-layouts.  A block moves one 32 x 32 (co x ci) tile with
+// all its taps through shared memory so that global reads AND writes are contiguous runs (the direct form reads the fp32
+// parameters with a stride of k*k or Cin*k*k elements and ran at ~1/8 of the copy bandwidth).
+constexpr int kPkT = 32;                                  // tile edge
+constexpr int kPkTaps = 9;                                // k <= 3
+constexpr int kPkLd = kPkT * kPkTaps + 1;                 // +1: conflict-free column reads
+
+__global__ void __launch_bounds__(256)
+pack_batched_kernel(const cy4_pack_item *__restrict__ items)
 {
+    __shared__ float t[kPkT][kPkLd];
     const cy4_pack_item it = items[blockIdx.y];
     const float *__restrict__ w = it.w_oihw;
-    const int k = it.ksize, Cin = it.Cin, Cout = it.Cout;
-    const int64_t kk = (int64_t)k * k;
-    if (it.w_fprop) {                       // [cout_pad][r][s][Cin]
-        __half *out = (__half *)it.w_fprop;
-        const int64_t total = (int64_t)it.cout_pad * kk * Cin;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int ci = (int)(i % Cin);
-            const int64_t r = i / Cin;
-            const int tap = (int)(r % kk);
-            const int co = (int)(r / kk);
-            out[i] = __float2half_rn(co < Cout ? w[((int64_t)co * Cin + ci) * kk + tap] * (it.fold_scale ? __ldg(it.fold_scale + co) : 1.f) : 0.f);
+    const int kk = it.ksize * it.ksize, Cin = it.Cin, Cout = it.Cout;
+    const int run = kPkT * kk;                            // floats of one co row inside the tile
+    const int tiles_ci = (it.cin_pad + kPkT - 1) / kPkT, tiles_co = (it.cout_pad + kPkT - 1) / kPkT;
+    __half *of = (__half *)it.w_fprop, *od = (__half *)it.w_dgrad;
+    for (int tile = blockIdx.x; tile < tiles_ci * tiles_co; tile += gridDim.x) {
+        const int co0 = (tile / tiles_ci) * kPkT, ci0 = (tile % tiles_ci) * kPkT;
+        for (int i = threadIdx.x; i < kPkT * run; i += 256) {
+            const int r = i / run, c = i - r * run;       // c = ci_local * kk + tap
+            const int co = co0 + r, ci = ci0 + c / kk;
+            t[r][c] = (co < Cout && ci < Cin) ? w[(int64_t)co * Cin * kk + (int64_t)ci0 * kk + c] : 0.f;
         }
-    }
-    if (it.w_dgrad) {                       // [cin_pad][r][s][cout_pad]
-        __half *out = (__half *)it.w_dgrad;
-        const int cp = it.cout_pad;
-        const int64_t total = (int64_t)it.cin_pad * kk * cp;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int co = (int)(i % cp);
-            const int64_t r = i / cp;
-            const int tap = (int)(r % kk);
-            const int ci = (int)(r / kk);
-            out[i] = __float2half_rn((co < Cout && ci < Cin) ? w[((int64_t)co * Cin + ci) * kk + tap] : 0.f);
+        __syncthreads();
+        if (of) {                                         // [cout_pad][tap][Cin]
+            for (int i = threadIdx.x; i < kPkT * run; i += 256) {
+                const int r = i / run, rem = i - r * run;
+                const int tap = rem / kPkT, ci = rem - tap * kPkT;
+                const int co = co0 + r;
+                if (co < it.cout_pad && ci0 + ci < Cin)
+                    of[((int64_t)co * kk + tap) * Cin + ci0 + ci] =
+                        __float2half_rn(t[r][ci * kk + tap] * ((it.fold_scale && co < Cout) ? __ldg(it.fold_scale + co) : 1.f));
+            }
         }
+        if (od) {                                         // [cin_pad][tap][cout_pad]
+            for (int i = threadIdx.x; i < kPkT * run; i += 256) {
+                const int cil = i / run, rem = i - cil * run;
+                const int tap = rem / kPkT, col = rem - tap * kPkT;
+                if (ci0 + cil < it.cin_pad && co0 + col < it.cout_pad)
+                    od[((int64_t)(ci0 + cil) * kk + tap) * it.cout_pad + co0 + col] = __float2half_rn(t[col][cil * kk + tap]);
+            }
+        }
+        __syncthreads();
     }
 }
 
-__global__ void unpack_batched_kernel(const cy4_unpack_item *__restrict__ items, const float *__restrict__ dscale)
+__global__ void __launch_bounds__(256)
+unpack_batched_kernel(const cy4_unpack_item *__restrict__ items, const float *__restrict__ dscale)
 {
+    __shared__ float t[kPkT][kPkLd];
     const cy4_unpack_item it = items[blockIdx.y];
     const float scale = dscale ? __ldg(dscale) : 1.f;
-    const int k = it.ksize, Cin = it.Cin;
-    const int64_t kk = (int64_t)k * k;
-    const int64_t total = (int64_t)it.Cout * Cin * kk;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % kk);
-        const int64_t r = i / kk;
-        const int ci = (int)(r % Cin);
-        const int co = (int)(r / Cin);
-        it.gw_oihw[i] = scale * it.dw_acc[((int64_t)co * kk + tap) * Cin + ci];
+    const int kk = it.ksize * it.ksize, Cin = it.Cin, Cout = it.Cout;
+    const int run = kPkT * kk;
+    const int tiles_ci = (Cin + kPkT - 1) / kPkT, tiles_co = (Cout + kPkT - 1) / kPkT;
+    for (int tile = blockIdx.x; tile < tiles_ci * tiles_co; tile += gridDim.x) {
+        const int co0 = (tile / tiles_ci) * kPkT, ci0 = (tile % tiles_ci) * kPkT;
+        for (int i = threadIdx.x; i < kPkT * run; i += 256) {       // read acc[co][tap][ci0 .. ci0+32): 32 contiguous floats
+            const int r = i / run, rem = i - r * run;
+            const int tap = rem / kPkT, ci = rem - tap * kPkT;
+            const int co = co0 + r;
+            t[r][ci * kk + tap] = (co < Cout && ci0 + ci < Cin) ? it.dw_acc[((int64_t)co * kk + tap) * Cin + ci0 + ci] : 0.f;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kPkT * run; i += 256) {       // write gw[co][ci0*kk .. (ci0+32)*kk): one contiguous run
+            const int r = i / run, c = i - r * run;
+            const int co = co0 + r;
+            if (co < Cout && ci0 + c / kk < Cin) it.gw_oihw[(int64_t)co * Cin * kk + (int64_t)ci0 * kk + c] = scale * t[r][c];
+        }
+        __syncthreads();
     }
 }
 
@@ -243,6 +271,44 @@ __global__ void stem_im2col_kernel(const float *__restrict__ x, int B, int C, in
     for (int i = 0; i < 4; ++i) dst[i] = src[i];
 }
 
+// The shape every complex-yolov4 cfg uses (3 channels, 3 x 3, pad 1): fully unrolled, so the 27 taps stay in registers (the generic
+// kernel's dynamically indexed row[] lives in local memory) and each (c, r, s) load is one coalesced 128-byte line per warp.
+template <int STRIDE>
+__global__ void __launch_bounds__(256)
+stem_im2col_c3k3_kernel(const float *__restrict__ x, int B, int H, int W, int Ho, int Wo, __half *__restrict__ cols)
+{
+    const int64_t M = (int64_t)B * Ho * Wo;
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int q = (int)(m % Wo);
+    const int pp = (int)((m / Wo) % Ho);
+    const int b = (int)(m / ((int64_t)Wo * Ho));
+    const float *xb = x + (int64_t)b * 3 * H * W;
+    float v[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int h = pp * STRIDE - 1 + r;
+        const bool hin = h >= 0 && h < H;
+#pragma unroll
+        for (int s_ = 0; s_ < 3; ++s_) {
+            const int w = q * STRIDE - 1 + s_;
+            const bool in = hin && w >= 0 && w < W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[(r * 3 + s_) * 3 + c] = in ? __ldg(xb + ((int64_t)c * H + h) * W + w) : 0.f;
+        }
+    }
+    uint4 *dst = (uint4 *)(cols + m * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 o; __half2 *ph = (__half2 *)&o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(v[i * 8 + 2 * j], v[i * 8 + 2 * j + 1]);
+        dst[i] = o;
+    }
+}
+
 }  // namespace cy4
 
 using namespace cy4;
@@ -256,6 +322,7 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
     if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
     if (!strcmp(name, "kblocks_per_slot")) { g_kps_max = value < 1 ? 1 : (value > 8 ? 8 : value); return 0; }
+    if (!strcmp(name, "conv1x1_matrix")) { g_conv1x1_matrix = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv_pair")) { g_conv_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "wgrad_variant")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_variant must be 1 or 2"); g_wgrad_variant = value; return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage
@@ -293,6 +360,7 @@ static int conv_fwd_impl(const cy4_conv_desc *d, const void *x, const void *w_fp
     g.bias = bias; g.ch_sum = ch_sum; g.ch_sqsum = ch_sqsum;
     g.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
     if (g.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_fwd: matrix mode needs a 1x1/s1/p0 conv");
+    if (g_conv1x1_matrix && k == 1 && d->stride == 1 && d->pad == 0) g.a_matrix = 1;
     if (epi) { g.epi_mode = epi->mode; g.epi_act = epi->act; g.epi_scale = epi->scale; g.epi_shift = epi->shift; g.side = epi->side; g.ld_side = epi->ld_side; }
     return run_generic(g, (cudaStream_t)stream);
 }
@@ -357,6 +425,7 @@ static int conv_dgrad_impl(const cy4_conv_desc *d, const void *dy, const void *w
         g.upper_w = g.upper_h = g.lower_w;               // Ho == Hi: the box spans Hi base pixels
         g.tstride = 1;
         g.Po = d->Hi; g.Qo = d->Wi;
+        if (g_conv1x1_matrix && k == 1) g.a_matrix = 1;
         g.ntaps = k * k;
         for (int o_r = 0; o_r < k; ++o_r)
             for (int o_s = 0; o_s < k; ++o_s) {
@@ -424,14 +493,14 @@ int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_
 int cy4_pack_weights_batched(const cy4_pack_item *items_dev, int n, void *stream)
 {
     CY4_CHECK_ARG(items_dev && n > 0, "cy4_pack_weights_batched: bad argument");
-    pack_batched_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(items_dev);
+    pack_batched_kernel<<<dim3(96, n), 256, 0, (cudaStream_t)stream>>>(items_dev);
     return cy4_launch_status("cy4_pack_weights_batched");
 }
 
 int cy4_unpack_wgrad_batched(const cy4_unpack_item *items_dev, int n, const float *dscale, void *stream)
 {
     CY4_CHECK_ARG(items_dev && n > 0, "cy4_unpack_wgrad_batched: bad argument");
-    unpack_batched_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(items_dev, dscale);
+    unpack_batched_kernel<<<dim3(96, n), 256, 0, (cudaStream_t)stream>>>(items_dev, dscale);
     return cy4_launch_status("cy4_unpack_wgrad_batched");
 }
 
@@ -440,6 +509,11 @@ int cy4_stem_im2col(const float *x_nchw, int B, int C, int H, int W, int ksize, 
     CY4_CHECK_ARG(x_nchw && cols && B > 0 && C > 0 && C * ksize * ksize <= 32, "cy4_stem_im2col: needs C*k*k <= 32");
     const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
     const int64_t M = (int64_t)B * Ho * Wo;
+    if (C == 3 && ksize == 3 && pad == 1 && (stride == 1 || stride == 2)) {
+        if (stride == 1) stem_im2col_c3k3_kernel<1><<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, B, H, W, Ho, Wo, (__half *)cols);
+        else stem_im2col_c3k3_kernel<2><<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, B, H, W, Ho, Wo, (__half *)cols);
+        return cy4_launch_status("cy4_stem_im2col");
+    }
     stem_im2col_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x_nchw, B, C, H, W, ksize, stride, pad, Ho, Wo, (__half *)cols);
     return cy4_launch_status("cy4_stem_im2col");
 }

@@ -305,3 +305,53 @@ def test_conv_variants(option, value):
         _lib.check(L.cy4_set_option(option.encode(), default))
     assert torch.equal(base[0], alt[0]) and torch.equal(base[1], alt[1])
     assert (base[2] - alt[2]).abs().max().item() <= 1e-3 * base[2].abs().max().item()     # split-K atomics: order only
+
+
+def test_batched_pack_and_unpack_match_the_single_layer_kernels():
+    """cy4_pack_weights_batched / cy4_unpack_wgrad_batched (tiled through shared memory, one launch for all layers, optional
+    BatchNorm fold scale) against the per-layer kernels and plain torch permutes."""
+    import ctypes
+    from cy4 import _lib, convops as co
+    from cy4._sigs_engine import PackItem, UnpackItem
+    L = _lib.lib()
+    torch.manual_seed(5)
+    shapes = [(64, 32, 3), (30, 256, 1), (128, 64, 1), (512, 256, 3), (96, 160, 3)]
+    ws = [torch.randn(o, i, k, k, device="cuda") for o, i, k in shapes]
+    scales = [torch.rand(o, device="cuda") + 0.5 if n % 2 else None for n, (o, i, k) in enumerate(shapes)]
+    rup = lambda x, m: (x + m - 1) // m * m
+    wf = [torch.full((rup(o, 32), k * k * i), 7.0, device="cuda", dtype=torch.float16) for o, i, k in shapes]
+    wd = [torch.full((rup(i, 32), k * k * rup(o, 32)), 7.0, device="cuda", dtype=torch.float16) for o, i, k in shapes]
+    items = []
+    for w, f, d, sc, (o, i, k) in zip(ws, wf, wd, scales, shapes):
+        it = PackItem()
+        it.w_oihw, it.w_fprop, it.w_dgrad = w.data_ptr(), f.data_ptr(), d.data_ptr()
+        it.Cout, it.Cin, it.ksize, it.cout_pad, it.cin_pad = o, i, k, rup(o, 32), rup(i, 32)
+        it.fold_scale = sc.data_ptr() if sc is not None else None
+        items.append(it)
+    arr = (PackItem * len(items))(*items)
+    table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().cuda()
+    _lib.check(L.cy4_pack_weights_batched(table.data_ptr(), len(items), _lib.stream()))
+    for w, f, d, sc, (o, i, k) in zip(ws, wf, wd, scales, shapes):
+        wsc = w * sc[:, None, None, None] if sc is not None else w
+        ref_f = torch.zeros(rup(o, 32), k * k * i, device="cuda")
+        ref_f[:o] = wsc.permute(0, 2, 3, 1).reshape(o, -1)
+        assert torch.equal(f, ref_f.half())
+        ref_d = torch.zeros(rup(i, 32), k * k, rup(o, 32), device="cuda")
+        ref_d[:i, :, :o] = w.permute(1, 2, 3, 0).reshape(i, k * k, o)
+        assert torch.equal(d, ref_d.reshape(rup(i, 32), -1).half())
+        if sc is None:
+            assert torch.equal(f, co.pack_fprop(w)) and torch.equal(d[:, :], co.pack_dgrad(torch.cat([w, torch.zeros(rup(o, 32) - o, i, k, k, device="cuda")])))
+    # unpack
+    accs = [torch.randn(rup(o, 32), k * k, i, device="cuda") for o, i, k in shapes]
+    gws = [torch.full((o, i, k, k), 3.0, device="cuda") for o, i, k in shapes]
+    uitems = []
+    for a, g, (o, i, k) in zip(accs, gws, shapes):
+        it = UnpackItem()
+        it.dw_acc, it.gw_oihw, it.Cout, it.Cin, it.ksize = a.data_ptr(), g.data_ptr(), o, i, k
+        uitems.append(it)
+    uarr = (UnpackItem * len(uitems))(*uitems)
+    utable = torch.frombuffer(bytearray(bytes(uarr)), dtype=torch.uint8).clone().cuda()
+    dscale = torch.tensor([0.25], device="cuda")
+    _lib.check(L.cy4_unpack_wgrad_batched(utable.data_ptr(), len(uitems), dscale.data_ptr(), _lib.stream()))
+    for a, g, (o, i, k) in zip(accs, gws, shapes):
+        assert torch.equal(g, 0.25 * a[:o].reshape(o, k, k, i).permute(0, 3, 1, 2))

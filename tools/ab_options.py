@@ -1,6 +1,6 @@
 """A/B timing of kernel options on the full training step (one process, same network and inputs).
     python tools/ab_options.py [batch]
-Prints ms/step for: defaults, conv_cluster=2, wgrad_cluster=2, kblocks_per_slot=1, CUDA-graph replay."""
+Prints ms/step for: defaults, the cy4_set_option tunables, the engine knobs (fused BN backward on/off), CUDA-graph replay."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "complex-yolov4-pytorch_b200"))
@@ -32,10 +32,10 @@ def timed(n=6, warm=3):
     return a.elapsed_time(b) / n
 
 
-base = {b"conv_cluster": 1, b"wgrad_cluster": 1, b"kblocks_per_slot": 4}
-for label, setting in [("defaults", {}), ("conv_cluster=2", {b"conv_cluster": 2}), ("wgrad_cluster=2", {b"wgrad_cluster": 2}),
-                       ("conv_cluster=2 wgrad_cluster=2", {b"conv_cluster": 2, b"wgrad_cluster": 2}),
-                       ("kblocks_per_slot=1", {b"kblocks_per_slot": 1}), ("defaults again", {})]:
+base = {b"conv_cluster": 1, b"wgrad_cluster": 1, b"kblocks_per_slot": 4, b"conv1x1_matrix": 0, b"conv_pair": 0, b"wgrad_variant": 1}
+for label, setting in [("defaults", {}), ("conv1x1_matrix=1", {b"conv1x1_matrix": 1}), ("conv_pair=1", {b"conv_pair": 1}),
+                       ("wgrad_variant=2", {b"wgrad_variant": 2}), ("conv_pair=1 wgrad_variant=2 conv1x1_matrix=1", {b"conv_pair": 1, b"wgrad_variant": 2, b"conv1x1_matrix": 1}),
+                       ("defaults again", {})]:
     for k, v in {**base, **setting}.items():
         L.cy4_set_option(k, v)
     print("%-34s %.3f ms/step" % (label, timed()), flush=True)
@@ -43,19 +43,8 @@ for k, v in base.items():
     L.cy4_set_option(k, v)
 net.use_cuda_graph = True
 print("%-34s %.3f ms/step" % ("defaults + CUDA graph", timed(warm=5)), flush=True)
-# experimental kernels last (a failure here must not hide the numbers above)
 net.use_cuda_graph = False
-try:
-    L.cy4_set_option(b"wgrad_variant", 2)
-    print("%-34s %.3f ms/step" % ("wgrad_variant=2 (persistent, experimental)", timed()), flush=True)
-except Exception as e:      # noqa: BLE001
-    print("wgrad_variant=2 failed:", repr(e)[:300], flush=True)
-finally:
-    L.cy4_set_option(b"wgrad_variant", 1)
-try:
-    L.cy4_set_option(b"conv_pair", 1)
-    print("%-34s %.3f ms/step" % ("conv_pair=1 (cta_group::2, experimental)", timed()), flush=True)
-except Exception as e:      # noqa: BLE001
-    print("conv_pair=1 failed:", repr(e)[:300], flush=True)
-finally:
-    L.cy4_set_option(b"conv_pair", 0)
+net.fuse_bn_backward = False
+print("%-34s %.3f ms/step" % ("fuse_bn_backward=False", timed()), flush=True)
+net.fuse_bn_backward = True
+print("%-34s %.3f ms/step" % ("fuse_bn_backward=True", timed()), flush=True)
