@@ -47,6 +47,40 @@ rbox_iou_matrix_kernel(const float *__restrict__ a6, int64_t n, const float *__r
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Anchor k-means distance matrix: utils/find_anchors.py:53-59 compute_iou for every (box, cluster)
+// pair.  Boxes and clusters are (w, l, yaw) centred at the origin.  Corners: kitti_bev_utils.get_corners evaluates them in
+// float64 and stores float32 (:96-120); polygons, areas and the intersection are float64 (shapely);
+// iou = inter / (box_area + cluster_area - inter + 1e-12) in float64, returned as float32 (np.array(..., dtype=np.float32)).
+__device__ __forceinline__ void kmeans_corners(double w, double l, double yaw, float cx[4], float cy[4])
+{
+    double sn, cs;
+    sincos(yaw, &sn, &cs);
+    cx[0] = (float)(0.0 - w / 2 * cs - l / 2 * sn);  cy[0] = (float)(0.0 - w / 2 * sn + l / 2 * cs);   // front left
+    cx[1] = (float)(0.0 - w / 2 * cs + l / 2 * sn);  cy[1] = (float)(0.0 - w / 2 * sn - l / 2 * cs);   // rear left
+    cx[2] = (float)(0.0 + w / 2 * cs + l / 2 * sn);  cy[2] = (float)(0.0 + w / 2 * sn - l / 2 * cs);   // rear right
+    cx[3] = (float)(0.0 + w / 2 * cs - l / 2 * sn);  cy[3] = (float)(0.0 + w / 2 * sn + l / 2 * cs);   // front right
+}
+__device__ __forceinline__ double quad_area64(const float x[4], const float y[4])
+{
+    double s = 0.0;
+    for (int i = 0; i < 4; ++i) { const int j = (i + 1) & 3; s += (double)x[i] * y[j] - (double)y[i] * x[j]; }
+    return fabs(s) * 0.5;
+}
+__global__ void __launch_bounds__(128)
+kmeans_iou_kernel(const double *__restrict__ boxes3, int64_t n, const double *__restrict__ clusters3, int k, float *__restrict__ ious)
+{
+    const int64_t total = n * k;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / k; const int j = (int)(t - i * k);
+        float ax[4], ay[4], bx[4], by[4];
+        kmeans_corners(boxes3[3 * i], boxes3[3 * i + 1], boxes3[3 * i + 2], ax, ay);
+        kmeans_corners(clusters3[3 * j], clusters3[3 * j + 1], clusters3[3 * j + 2], bx, by);
+        const double inter = convex_inter64(ax, ay, bx, by);
+        ious[t] = (float)(inter / (quad_area64(ax, ay) + quad_area64(bx, by) - inter + 1e-12));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // post_processing_v2: one CTA per image.
 //   1. rows with conf >= conf_thresh are compacted (any order), score = conf * max(cls)         (:333-339)
 //   2. sorted by score, descending; equal scores keep the lower row index first (the reference's
@@ -251,6 +285,17 @@ int cy4_rbox_iou_matrix(const float *a6, int64_t n, const float *b6, int64_t m, 
     const int grid = (int)std::min<int64_t>((total + 127) / 128, (int64_t)sm_count() * 16);
     rbox_iou_matrix_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a6, n, b6, m, ious);
     return cy4_launch_status("cy4_rbox_iou_matrix");
+}
+
+int cy4_kmeans_iou(const double *boxes3, int64_t n, const double *clusters3, int k, float *ious, void *stream)
+{
+    CY4_CHECK_ARG(n >= 0 && k >= 0, "cy4_kmeans_iou: negative size");
+    if (n == 0 || k == 0) return 0;
+    CY4_CHECK_ARG(boxes3 && clusters3 && ious, "cy4_kmeans_iou: null pointer");
+    const int64_t total = n * k;
+    const int grid = (int)std::min<int64_t>((total + 127) / 128, (int64_t)sm_count() * 16);
+    kmeans_iou_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(boxes3, n, clusters3, k, ious);
+    return cy4_launch_status("cy4_kmeans_iou");
 }
 
 int cy4_nms_max_candidates(void) { return kNmsMaxCand; }

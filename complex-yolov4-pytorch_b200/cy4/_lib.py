@@ -49,6 +49,7 @@ _SIGS = {
                                         c_i64, c_i64, c_i64, c_i64, c_vp]),
     # evaluation
     "cy4_rbox_iou_matrix": (ctypes.c_int, [c_f, c_i64, c_f, c_i64, c_f, c_vp]),
+    "cy4_kmeans_iou": (ctypes.c_int, [c_f, c_i64, c_f, ctypes.c_int, c_f, c_vp]),
     "cy4_nms_max_candidates": (ctypes.c_int, []),
     "cy4_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "cy4_nms_rotated_v2": (ctypes.c_int, [c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, c_f,

@@ -266,6 +266,11 @@ CY4_API int cy4_colsum_f32(const float *src, int64_t lds, int64_t M, int C, floa
  * ious[i*m + j] = IoU(a6[i], b6[j]); rows (x, y, w, l, im, re).  fp32 corners, fp64 polygon intersection
  * (shapely in the reference), iou = reciprocal(area_a + area_b - inter + 1e-16) * inter in fp32. */
 CY4_API int cy4_rbox_iou_matrix(const float *a6, int64_t n, const float *b6, int64_t m, float *ious, void *stream);
+/* Anchor k-means distance matrix (utils/find_anchors.py:53-59 compute_iou for all boxes at once):
+ * ious[i*k + j] = IoU of box i and cluster j, both (w, l, yaw) float64 rows centred at the origin.  Corners as
+ * kitti_bev_utils.get_corners (float64 arithmetic stored as float32), polygon areas / intersection / ratio in float64
+ * (shapely), + 1e-12 in the denominator, result rounded to float32 like the reference's np.float32 array. */
+CY4_API int cy4_kmeans_iou(const double *boxes3, int64_t n, const double *clusters3, int k, float *ious, void *stream);
 
 /* utils/evaluation_utils.py:322-357 post_processing_v2 on the device, one CTA per image.
  * pred [B, N, 7+nC] (x,y,w,l,im,re,conf,cls...); rows with conf >= conf_thresh, sorted by conf*max(cls)

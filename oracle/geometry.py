@@ -40,6 +40,8 @@ def lib():
         L.orc_rgiou_pairs.argtypes = [fp, fp, ctypes.c_int64, ctypes.c_uint32, fp, fp, fp]
         L.orc_rgiou_pairs_exact64.argtypes = [fp, fp, ctypes.c_int64, dp, dp]
         L.orc_iou_matrix.argtypes = [fp, ctypes.c_int64, fp, ctypes.c_int64, fp]
+        L.orc_kmeans_iou.argtypes = [dp, ctypes.c_int64, dp, ctypes.c_int, fp]
+        L.orc_kmeans_iou.restype = None
         _lib = L
     return _lib
 
@@ -109,4 +111,15 @@ def iou_matrix(a6, b6):
     out = np.zeros((a.shape[0], b.shape[0]), np.float32)
     if a.shape[0] and b.shape[0]:
         lib().orc_iou_matrix(_p(a), a.shape[0], _p(b), b.shape[0], _p(out))
+    return out
+
+
+def kmeans_iou(boxes3, clusters3):
+    """find_anchors.py:53-59 for all pairs: [n,3] x [k,3] float64 (w, l, yaw) -> float32 [n,k]."""
+    b = np.ascontiguousarray(np.asarray(boxes3, np.float64)).reshape(-1, 3)
+    c = np.ascontiguousarray(np.asarray(clusters3, np.float64)).reshape(-1, 3)
+    out = np.zeros((b.shape[0], c.shape[0]), np.float32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    if b.shape[0] and c.shape[0]:
+        lib().orc_kmeans_iou(b.ctypes.data_as(dp), b.shape[0], c.ctypes.data_as(dp), c.shape[0], _p(out))
     return out

@@ -266,6 +266,42 @@ void orc_iou_matrix(const float *a6, int64_t n, const float *b6, int64_t m, floa
     }
 }
 
+/* utils/find_anchors.py:53-59 compute_iou for every (box, cluster) pair.  Rows (w, l, yaw) float64,
+ * boxes centred at the origin.  Corners: data_process/kitti_bev_utils.py:96-120 get_corners -- float64 arithmetic stored into a
+ * float32 array; polygon areas and the intersection in float64 (shapely); iou = inter / (a1 + a2 - inter + 1e-12) in float64,
+ * stored as float32 (np.array(iou, dtype=np.float32)). */
+static void kmeans_corners(double w, double l, double yaw, float c[4][2])
+{
+    double cs = cos(yaw), sn = sin(yaw);
+    c[0][0] = (float)(0.0 - w / 2 * cs - l / 2 * sn);  c[0][1] = (float)(0.0 - w / 2 * sn + l / 2 * cs);
+    c[1][0] = (float)(0.0 - w / 2 * cs + l / 2 * sn);  c[1][1] = (float)(0.0 - w / 2 * sn - l / 2 * cs);
+    c[2][0] = (float)(0.0 + w / 2 * cs + l / 2 * sn);  c[2][1] = (float)(0.0 + w / 2 * sn - l / 2 * cs);
+    c[3][0] = (float)(0.0 + w / 2 * cs - l / 2 * sn);  c[3][1] = (float)(0.0 + w / 2 * sn + l / 2 * cs);
+}
+static double quad_area64(const float c[4][2])
+{
+    double s = 0.0;
+    int i;
+    for (i = 0; i < 4; ++i) { int j = (i + 1) & 3; s += (double)c[i][0] * c[j][1] - (double)c[i][1] * c[j][0]; }
+    return fabs(s) * 0.5;
+}
+void orc_kmeans_iou(const double *boxes3, int64_t n, const double *clusters3, int k, float *ious)
+{
+    int64_t i;
+    int j;
+    for (i = 0; i < n; ++i) {
+        float bc[4][2];
+        kmeans_corners(boxes3[3 * i], boxes3[3 * i + 1], boxes3[3 * i + 2], bc);
+        double ba = quad_area64(bc);
+        for (j = 0; j < k; ++j) {
+            float cc[4][2];
+            kmeans_corners(clusters3[3 * j], clusters3[3 * j + 1], clusters3[3 * j + 2], cc);
+            double inter = clip_area64(bc, cc);
+            ious[i * k + j] = (float)(inter / (ba + quad_area64(cc) - inter + 1e-12));
+        }
+    }
+}
+
 /* utils/iou_rotated_boxes_utils.py:98-142  iou_pred_vs_target_boxes, element-wise pairs.
  * flags bit0: GIoU (reference clipper :122 + hull term :128-133); otherwise the shapely path
  * (:118-120, exact intersection) with term = 1 - iou (:135).
