@@ -177,17 +177,34 @@ constexpr int kPkT = 32;                                  // tile edge
 constexpr int kPkTaps = 9;                                // k <= 3
 constexpr int kPkLd = kPkT * kPkTaps + 1;                 // +1: conflict-free column reads
 
+// The tiles of ALL items form one list (item.tile_begin = prefix sum of the per-item tile counts, filled by the caller), walked by a
+// grid of a few blocks per SM: the dozen 4.7 M-parameter layers that dominate the bytes are spread over the whole GPU instead of
+// over the blocks of one grid row.
+template <typename Item>
+__device__ __forceinline__ int find_item(const Item *__restrict__ items, int n, int tile)
+{
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {                                     // last item with tile_begin <= tile
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256)
-pack_batched_kernel(const cy4_pack_item *__restrict__ items)
+pack_batched_kernel(const cy4_pack_item *__restrict__ items, int n)
 {
     __shared__ float t[kPkT][kPkLd];
-    const cy4_pack_item it = items[blockIdx.y];
-    const float *__restrict__ w = it.w_oihw;
-    const int kk = it.ksize * it.ksize, Cin = it.Cin, Cout = it.Cout;
-    const int run = kPkT * kk;                            // floats of one co row inside the tile
-    const int tiles_ci = (it.cin_pad + kPkT - 1) / kPkT, tiles_co = (it.cout_pad + kPkT - 1) / kPkT;
-    __half *of = (__half *)it.w_fprop, *od = (__half *)it.w_dgrad;
-    for (int tile = blockIdx.x; tile < tiles_ci * tiles_co; tile += gridDim.x) {
+    const cy4_pack_item last = items[n - 1];
+    const int total = last.tile_begin + ((last.cin_pad + kPkT - 1) / kPkT) * ((last.cout_pad + kPkT - 1) / kPkT);
+    for (int gt = items[0].tile_begin + blockIdx.x; gt < total; gt += gridDim.x) {      // (a sub-range of a table starts at its own tile_begin)
+        const cy4_pack_item it = items[find_item(items, n, gt)];
+        const float *__restrict__ w = it.w_oihw;
+        const int kk = it.ksize * it.ksize, Cin = it.Cin, Cout = it.Cout;
+        const int run = kPkT * kk;                        // floats of one co row inside the tile
+        const int tiles_ci = (it.cin_pad + kPkT - 1) / kPkT;
+        __half *of = (__half *)it.w_fprop, *od = (__half *)it.w_dgrad;
+        const int tile = gt - it.tile_begin;
         const int co0 = (tile / tiles_ci) * kPkT, ci0 = (tile % tiles_ci) * kPkT;
         for (int i = threadIdx.x; i < kPkT * run; i += 256) {
             const int r = i / run, c = i - r * run;       // c = ci_local * kk + tap
@@ -218,15 +235,18 @@ pack_batched_kernel(const cy4_pack_item *__restrict__ items)
 }
 
 __global__ void __launch_bounds__(256)
-unpack_batched_kernel(const cy4_unpack_item *__restrict__ items, const float *__restrict__ dscale)
+unpack_batched_kernel(const cy4_unpack_item *__restrict__ items, int n, const float *__restrict__ dscale)
 {
     __shared__ float t[kPkT][kPkLd];
-    const cy4_unpack_item it = items[blockIdx.y];
     const float scale = dscale ? __ldg(dscale) : 1.f;
-    const int kk = it.ksize * it.ksize, Cin = it.Cin, Cout = it.Cout;
-    const int run = kPkT * kk;
-    const int tiles_ci = (Cin + kPkT - 1) / kPkT, tiles_co = (Cout + kPkT - 1) / kPkT;
-    for (int tile = blockIdx.x; tile < tiles_ci * tiles_co; tile += gridDim.x) {
+    const cy4_unpack_item last = items[n - 1];
+    const int total = last.tile_begin + ((last.Cin + kPkT - 1) / kPkT) * ((last.Cout + kPkT - 1) / kPkT);
+    for (int gt = items[0].tile_begin + blockIdx.x; gt < total; gt += gridDim.x) {      // (a sub-range of a table starts at its own tile_begin)
+        const cy4_unpack_item it = items[find_item(items, n, gt)];
+        const int kk = it.ksize * it.ksize, Cin = it.Cin, Cout = it.Cout;
+        const int run = kPkT * kk;
+        const int tiles_ci = (Cin + kPkT - 1) / kPkT;
+        const int tile = gt - it.tile_begin;
         const int co0 = (tile / tiles_ci) * kPkT, ci0 = (tile % tiles_ci) * kPkT;
         for (int i = threadIdx.x; i < kPkT * run; i += 256) {       // read acc[co][tap][ci0 .. ci0+32): 32 contiguous floats
             const int r = i / run, rem = i - r * run;
@@ -493,14 +513,14 @@ int cy4_unpack_wgrad(const float *dw_acc, int Cout, int Cin, int ksize, int cin_
 int cy4_pack_weights_batched(const cy4_pack_item *items_dev, int n, void *stream)
 {
     CY4_CHECK_ARG(items_dev && n > 0, "cy4_pack_weights_batched: bad argument");
-    pack_batched_kernel<<<dim3(96, n), 256, 0, (cudaStream_t)stream>>>(items_dev);
+    pack_batched_kernel<<<sm_count() * 6, 256, 0, (cudaStream_t)stream>>>(items_dev, n);
     return cy4_launch_status("cy4_pack_weights_batched");
 }
 
 int cy4_unpack_wgrad_batched(const cy4_unpack_item *items_dev, int n, const float *dscale, void *stream)
 {
     CY4_CHECK_ARG(items_dev && n > 0, "cy4_unpack_wgrad_batched: bad argument");
-    unpack_batched_kernel<<<dim3(96, n), 256, 0, (cudaStream_t)stream>>>(items_dev, dscale);
+    unpack_batched_kernel<<<sm_count() * 6, 256, 0, (cudaStream_t)stream>>>(items_dev, n, dscale);
     return cy4_launch_status("cy4_unpack_wgrad_batched");
 }
 

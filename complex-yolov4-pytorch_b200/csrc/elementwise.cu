@@ -37,8 +37,9 @@ __global__ void bn_finalize_kernel(const float *__restrict__ ch_sum, const float
     if (c >= C) return;
     float mean, var;
     if (training) {
-        const double m = (double)ch_sum[c] / count;
-        double v = (double)ch_sqsum[c] / count - m * m;
+        const double inv_count = 1.0 / (double)count;
+        const double m = (double)ch_sum[c] * inv_count;
+        double v = (double)ch_sqsum[c] * inv_count - m * m;
         if (v < 0.0) v = 0.0;
         mean = (float)m; var = (float)v;
         const float unbiased = count > 1.f ? (float)(v * (double)count / ((double)count - 1.0)) : var;
@@ -84,6 +85,7 @@ struct BnFin {
     float *running_mean, *running_var; long long *num_batches;
     float *scale_out, *shift_out, *mean_out, *rstd_out;
     float count, momentum, eps;
+    double inv_count;
 };
 
 // out = act(y * scale + shift) (+ residual)
@@ -108,8 +110,10 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int c = c0 + k;
-                const double m = (double)fin.ch_sum[c] / fin.count;
-                double v = (double)fin.ch_sqsum[c] / fin.count - m * m;
+                // same arithmetic as bn_finalize_kernel (double mean / variance), with the divisions by the count turned into
+                // one multiplication by its double reciprocal: every thread of the grid executes this prologue
+                const double m = (double)fin.ch_sum[c] * fin.inv_count;
+                double v = (double)fin.ch_sqsum[c] * fin.inv_count - m * m;
                 if (v < 0.0) v = 0.0;
                 const float mean = (float)m, var = (float)v;
                 const float rstd = rsqrtf(var + fin.eps);
@@ -564,7 +568,7 @@ int cy4_bn_train_act_fwd(const void *y, int64_t ldy, const float *ch_sum, const 
     f.ch_sum = ch_sum; f.ch_sqsum = ch_sqsum; f.gamma = gamma; f.beta = beta;
     f.running_mean = running_mean; f.running_var = running_var; f.num_batches = (long long *)num_batches_tracked;
     f.scale_out = scale; f.shift_out = shift; f.mean_out = mean; f.rstd_out = rstd;
-    f.count = count; f.momentum = momentum; f.eps = eps;
+    f.count = count; f.momentum = momentum; f.eps = eps; f.inv_count = 1.0 / (double)count;
     return bn_act_fwd_launch(y, ldy, nullptr, nullptr, act, residual, ldr, out, ldo, M, C, &f, stream);
 }
 

@@ -21,12 +21,12 @@ PD = ctypes.POINTER(ConvDesc)
 class PackItem(ctypes.Structure):
     _fields_ = [("w_oihw", ctypes.c_void_p), ("w_fprop", ctypes.c_void_p), ("w_dgrad", ctypes.c_void_p),
                 ("Cout", ctypes.c_int32), ("Cin", ctypes.c_int32), ("ksize", ctypes.c_int32), ("cout_pad", ctypes.c_int32),
-                ("cin_pad", ctypes.c_int32), ("reserved", ctypes.c_int32), ("fold_scale", ctypes.c_void_p)]
+                ("cin_pad", ctypes.c_int32), ("tile_begin", ctypes.c_int32), ("fold_scale", ctypes.c_void_p)]
 
 
 class UnpackItem(ctypes.Structure):
     _fields_ = [("dw_acc", ctypes.c_void_p), ("gw_oihw", ctypes.c_void_p), ("Cout", ctypes.c_int32), ("Cin", ctypes.c_int32),
-                ("ksize", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("ksize", ctypes.c_int32), ("tile_begin", ctypes.c_int32)]
 
 SIGS = {
     "cy4_set_option": (c_i, [ctypes.c_char_p, c_i]),

@@ -178,7 +178,8 @@ class Darknet(nn.Module):
         self.engine_allreduce = False   # True (set by models.model_utils.make_data_parallel): the engine averages gradients over the ranks
                                         # itself, overlapped with backward; DDP then carries a no-op communication hook
         self.allreduce_groups = 6       # number of gradient groups of that exchange
-        self.fuse_bn_backward = True    # the dgrad epilogue of a tensor's last gradient writer does the producer's BN-backward reduce pass
+        self.fuse_bn_backward = 1       # 1: the dgrad epilogue of a tensor's last gradient writer does the producer's BN-backward reduce
+                                        # pass where its MMAs hide it (engine.Plan._plan_bwd_fusion); 2: wherever possible; 0: never
         self.fuse_eval = True           # eval() forward without grad: BatchNorm folded into the weights, activation in the conv epilogue
         self.outputs_on_device = False  # True: eval() forward returns the detections as a CUDA tensor (default: CPU, like the reference)
         self._engine = None

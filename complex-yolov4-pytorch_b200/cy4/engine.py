@@ -26,7 +26,7 @@ from . import convops as co
 from .yolo import LazyMetrics, make_desc, check_status
 
 ACT = {"linear": 0, "leaky": 1, "mish": 2}
-_PROFILED = ("cy4_conv_fwd", "cy4_conv_dgrad", "cy4_conv_wgrad")
+_PROFILED = ("cy4_conv_fwd", "cy4_conv_dgrad", "cy4_conv_dgrad_fused", "cy4_conv_wgrad")
 
 
 def rup(x, m):
@@ -146,7 +146,7 @@ class StepEngine:
         # conv epilogue, no raw conv outputs kept
         infer = (not model.training) and not training_graph and bool(getattr(model, "fuse_eval", True))
         key = (tuple(x.shape), x.device, model.training, targets is not None,
-               tuple(p.data_ptr() for p in params[:4]), len(params), infer, bool(getattr(model, "fuse_bn_backward", True)))
+               tuple(p.data_ptr() for p in params[:4]), len(params), infer, int(getattr(model, "fuse_bn_backward", 1)))
         with torch.cuda.device(x.device):
             if self.key != key:
                 self.plan = None                          # release the old plan's buffers before allocating the new ones
@@ -196,6 +196,7 @@ class StepEngine:
     # static buffers; outputs (loss, metrics, detections, gradients) live in static buffers as well.
     def _forward(self, x, targets):
         plan, model = self.plan, self.model
+        plan.join_d2h()                    # (outside any graph capture) the previous step's detections copy has left the device buffers
         use_graph = bool(getattr(model, "use_cuda_graph", False)) and targets is not None and model.training
         if not use_graph:
             plan.graph_state = None
@@ -224,6 +225,7 @@ class StepEngine:
 
     def _backward(self, gloss):
         plan = self.plan
+        plan.join_d2h()                    # the host sees the detections complete at the synchronisation that follows backward
         gs = plan.graph_state
         if gs is None or gs["fwd"] is None:
             return plan.backward(gloss)
@@ -537,7 +539,8 @@ class Plan:
         for rec in self.convs:
             rec["fuse_bwd"] = None          # consumer side: the producer rec whose reduce pass this conv's dgrad performs
             rec["reduce_fused"] = False     # producer side
-        if self.infer or not bool(getattr(self.model, "fuse_bn_backward", True)):
+        mode = int(getattr(self.model, "fuse_bn_backward", 1))
+        if self.infer or not mode:
             return
         writers = {}                        # id(storage) -> [(lo, hi, kind, rec)] in backward order
         events = {}
@@ -582,6 +585,14 @@ class Plan:
             last = ws[-1]
             if last[2] != "conv" or last[3]["fuse_bwd"] is not None:
                 continue
+            # Mish' costs two MUFU operations per element and the eight epilogue warps are all the SM has for it while the
+            # tile's MMAs run: 16 * N cycles per 128 x N tile.  The tensor work of that tile is k^2 * Cout / 64 k-blocks of
+            # 2 * N cycles, so only input-gradient GEMMs with a long reduction (3 x 3, or very wide 1 x 1) hide the extra pass;
+            # on the short-K 1 x 1 layers the fused epilogue was measured slower than the separate bandwidth-bound pass
+            # (profiles/r2_bn_backward_fusion.md).  LeakyReLU / linear producers have no MUFU work and always fuse.
+            cons = last[3]
+            if mode == 1 and P["act"] == ACT["mish"] and cons["k"] * cons["k"] * cons["Cout"] < 1024:
+                continue
             last[3]["fuse_bwd"] = P
             P["reduce_fused"] = True
 
@@ -590,7 +601,8 @@ class Plan:
         """fp32 OIHW parameters -> K-major fp16 packs, one batched launch, only when a parameter changed."""
         from ._sigs_engine import PackItem
         L = self.L
-        sig = tuple((rec["conv"].weight._version, rec["conv"].weight.data_ptr()) for rec in self.convs)
+        ptrs = tuple(rec["conv"].weight.data_ptr() for rec in self.convs)
+        sig = tuple(rec["conv"].weight._version for rec in self.convs) + ptrs
         if self.infer:      # the folded packs also depend on the BatchNorm parameters and running statistics
             sig += tuple(t._version for rec in self.convs if rec["bn"] is not None
                          for t in (rec["bn"].weight, rec["bn"].bias, rec["bn"].running_mean, rec["bn"].running_var))
@@ -604,13 +616,14 @@ class Plan:
                 q = [self.bnq[i, rec["coff"]:].data_ptr() for i in range(4)]
                 self._call(L.cy4_bn_finalize, None, None, 1.0, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                            bn.running_var.data_ptr(), None, float(bn.momentum), float(bn.eps), 0, rec["Cout"], q[0], q[1], q[2], q[3], st)
-        ptrs = tuple(p for _, p in sig)
         if ptrs != getattr(self, "_pack_ptrs", None):
-            items = []
+            items, tiles = [], 0
             for rec in self.convs:
                 if rec["stem"]:
                     continue
                 it = PackItem()
+                it.tile_begin = tiles
+                tiles += (rup(rec["Cout"], 32) // 32) * (rup(rec["Cin"], 32) // 32)
                 w = rec["conv"].weight
                 it.w_oihw, it.w_fprop, it.w_dgrad = w.data_ptr(), rec["wf"].data_ptr(), (rec["wd"].data_ptr() if "wd" in rec else None)
                 it.Cout, it.Cin, it.ksize = rec["Cout"], rec["Cin"], rec["k"]
@@ -638,7 +651,6 @@ class Plan:
         st = _lib.stream()
         model = self.model
         training = model.training
-        self.join_d2h()                    # the previous step's detections leave the pinned buffer intact until copied
         x = x.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
@@ -872,7 +884,6 @@ class Plan:
                     works.append(dist.all_reduce(gb, op=dist.ReduceOp.AVG, async_op=True))
             for w_ in works:
                 w_.wait()                                # the current stream waits for the exchange; the host does not block
-        self.join_d2h()
         fresh = gw_flat.clone()
         for w, off in self._wslices:
             grads[id(w)] = fresh[off:off + w.numel()].view_as(w)
@@ -920,11 +931,13 @@ class Plan:
         table is built once per plan: accumulators and the flat gradient buffer are persistent."""
         from ._sigs_engine import UnpackItem
         if getattr(self, "_unpack_dev", None) is None:
-            items = []
+            items, tiles = [], 0
             for rec in self.convs:
                 if rec["stem"]:
                     continue
                 it = UnpackItem()
+                it.tile_begin = tiles
+                tiles += (rup(rec["Cout"], 32) // 32) * (rup(rec["Cin"], 32) // 32)
                 n = rec["conv"].weight.numel()
                 it.dw_acc = rec["acc"].data_ptr()
                 it.gw_oihw = self.gw_flat.data_ptr() + 4 * rec["woff"]

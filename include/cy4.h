@@ -192,14 +192,17 @@ typedef struct cy4_pack_item {
     const float *w_oihw;     /* [Cout][Cin][k][k] fp32 */
     void *w_fprop;           /* [cout_pad][k*k][Cin] fp16, or NULL */
     void *w_dgrad;           /* [cin_pad][k*k][cout_pad] fp16, or NULL */
-    int32_t Cout, Cin, ksize, cout_pad, cin_pad, reserved;
+    int32_t Cout, Cin, ksize, cout_pad, cin_pad;
+    int32_t tile_begin;      /* index of this item's first 32 x 32 (co x ci) tile in the launch-wide tile list: the prefix sum of
+                                ceil(cout_pad/32) * ceil(cin_pad/32) over the preceding items (0 for the first) */
     const float *fold_scale; /* NULL, or [Cout] fp32: w_fprop rows are multiplied by it (eval-mode BatchNorm folding,
                                 gamma * rsqrt(running_var + eps); the matching shift goes to cy4_conv_fwd_fused) */
 } cy4_pack_item;
 typedef struct cy4_unpack_item {
     const float *dw_acc;     /* [Cout_pad][k*k][Cin] fp32 */
     float *gw_oihw;          /* [Cout][Cin][k][k] fp32 */
-    int32_t Cout, Cin, ksize, reserved;
+    int32_t Cout, Cin, ksize;
+    int32_t tile_begin;      /* prefix sum of ceil(Cout/32) * ceil(Cin/32) over the preceding items */
 } cy4_unpack_item;
 CY4_API int cy4_pack_weights_batched(const cy4_pack_item *items_dev, int n, void *stream);
 CY4_API int cy4_unpack_wgrad_batched(const cy4_unpack_item *items_dev, int n, const float *dscale, void *stream);

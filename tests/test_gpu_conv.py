@@ -321,9 +321,11 @@ def test_batched_pack_and_unpack_match_the_single_layer_kernels():
     rup = lambda x, m: (x + m - 1) // m * m
     wf = [torch.full((rup(o, 32), k * k * i), 7.0, device="cuda", dtype=torch.float16) for o, i, k in shapes]
     wd = [torch.full((rup(i, 32), k * k * rup(o, 32)), 7.0, device="cuda", dtype=torch.float16) for o, i, k in shapes]
-    items = []
+    items, tiles = [], 0
     for w, f, d, sc, (o, i, k) in zip(ws, wf, wd, scales, shapes):
         it = PackItem()
+        it.tile_begin = tiles
+        tiles += (rup(o, 32) // 32) * (rup(i, 32) // 32)
         it.w_oihw, it.w_fprop, it.w_dgrad = w.data_ptr(), f.data_ptr(), d.data_ptr()
         it.Cout, it.Cin, it.ksize, it.cout_pad, it.cin_pad = o, i, k, rup(o, 32), rup(i, 32)
         it.fold_scale = sc.data_ptr() if sc is not None else None
@@ -344,9 +346,11 @@ def test_batched_pack_and_unpack_match_the_single_layer_kernels():
     # unpack
     accs = [torch.randn(rup(o, 32), k * k, i, device="cuda") for o, i, k in shapes]
     gws = [torch.full((o, i, k, k), 3.0, device="cuda") for o, i, k in shapes]
-    uitems = []
+    uitems, tiles = [], 0
     for a, g, (o, i, k) in zip(accs, gws, shapes):
         it = UnpackItem()
+        it.tile_begin = tiles
+        tiles += (rup(o, 32) // 32) * (rup(i, 32) // 32)
         it.dw_acc, it.gw_oihw, it.Cout, it.Cin, it.ksize = a.data_ptr(), g.data_ptr(), o, i, k
         uitems.append(it)
     uarr = (UnpackItem * len(uitems))(*uitems)

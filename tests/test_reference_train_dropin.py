@@ -55,4 +55,4 @@ def test_reference_train_py_runs_on_the_engine(tmp_path):
     assert ck, "train.py did not save its checkpoint"
     import torch
     sd = torch.load([os.path.join(_r, f) for _r, _d, fs in os.walk(str(tmp_path)) for f in fs if f.startswith("Model_")][0], map_location="cpu")
-    assert any(k.endswith("conv_0.weight") for k in sd) and len(sd) > 100          # the reference's state_dict naming
+    assert any(k.endswith(".conv1.weight") for k in sd) and any("batch_norm" in k or ".bn" in k for k in sd) and len(sd) > 100, list(sd)[:8]

@@ -42,9 +42,11 @@ for label, setting in [("defaults", {}), ("conv1x1_matrix=1", {b"conv1x1_matrix"
 for k, v in base.items():
     L.cy4_set_option(k, v)
 net.use_cuda_graph = True
-print("%-34s %.3f ms/step" % ("defaults + CUDA graph", timed(warm=5)), flush=True)
+try:
+    print("%-34s %.3f ms/step" % ("defaults + CUDA graph", timed(warm=5)), flush=True)
+except Exception as e:      # noqa: BLE001
+    print("CUDA graph replay failed:", repr(e)[:300], flush=True)
 net.use_cuda_graph = False
-net.fuse_bn_backward = False
-print("%-34s %.3f ms/step" % ("fuse_bn_backward=False", timed()), flush=True)
-net.fuse_bn_backward = True
-print("%-34s %.3f ms/step" % ("fuse_bn_backward=True", timed()), flush=True)
+for mode in (0, 2, 1):
+    net.fuse_bn_backward = mode
+    print("%-34s %.3f ms/step" % ("fuse_bn_backward=%d" % mode, timed()), flush=True)
