@@ -23,8 +23,7 @@ int g_disable_tma_out = getenv("CY4_NO_TMA_OUT") != nullptr;
 int g_cluster = getenv("CY4_CLUSTER") ? atoi(getenv("CY4_CLUSTER")) : 1;
 int g_debug = 0;
 int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disables the packing)
-int g_conv_pair = 0;        // 1: experimental CTA-pair (cta_group::2) conv kernel for the eligible launches (conv_pair.cu), not yet measured
-int g_wgrad_variant = 1;    // 2: experimental persistent kernel (conv_wgrad2.cu), not yet measured
+int g_conv_pair = 1;        // CTA-pair (cta_group::2) conv kernel for the eligible launches (conv_pair.cu); 0: always the 1-CTA kernel
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
@@ -79,7 +78,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     // clusters of 2 CTAs share each weight slab through TMA multicast (halves the L2 -> SM weight traffic)
     p.cluster = (p.tiles_m >= 2 && g_cluster >= 2) ? 2 : 1;
     if (g_cluster >= 4 && p.tiles_m >= 8 && p.block_n >= 64) p.cluster = 4;
-    const bool pair = g_conv_pair && conv_pair_eligible(p) && p.epi_mode == EPI_NONE;
+    const bool pair = g_conv_pair && conv_pair_eligible(p);
     if (pair) p.cluster = 2;             // weight box of block_n / 2 rows: each CTA of the pair loads its half
     rc = make_tmap_2d(&tmB, g.w, (uint64_t)g.w_ktot, (uint64_t)g.w_rows_pad, (uint64_t)g.w_ktot * 2, p.kchunk, p.block_n / p.cluster, swz, 0);
     if (rc) return rc;
@@ -344,7 +343,6 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "kblocks_per_slot")) { g_kps_max = value < 1 ? 1 : (value > 8 ? 8 : value); return 0; }
     if (!strcmp(name, "conv1x1_matrix")) { g_conv1x1_matrix = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv_pair")) { g_conv_pair = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "wgrad_variant")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_variant must be 1 or 2"); g_wgrad_variant = value; return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage
     set_error("cy4_set_option: unknown option %s", name);
     return -1;

@@ -1,5 +1,6 @@
-// conv_pair.cu -- EXPERIMENTAL CTA-pair (tcgen05 cta_group::2) variant of the implicit-GEMM convolution
-// (cy4_set_option("conv_pair", 1); default off, NOT yet run on hardware -- DESIGN.md section 4.3, lever 1).
+// conv_pair.cu -- CTA-pair (tcgen05 cta_group::2) variant of the implicit-GEMM convolution, used for every eligible launch
+// (kchunk 64, N tile 128 / 256, >= 2 m tiles; cy4_set_option("conv_pair", 0) falls back to conv_tc.cu).  Measured on B200
+// (profiles/r2_conv_shape_bench.md): never slower than the 1-CTA kernel, -27 % on the 128-channel 3x3 layers.
 //
 // conv_tc.cu's 128 x block_n tiles are bound by the L2 -> shared-memory ingest of their operand slabs
 // (48 KB per 512 tensor cycles for N = 256).  Here two CTAs on the SMs of one TPC work
@@ -18,12 +19,13 @@
 //   * the epilogue warps of both CTAs release an accumulator stage by arriving on the LEADER's tmem_empty
 //     barrier (count 8);
 //   * TMEM is allocated / freed with the cta_group::2 forms by warp 1 of both CTAs.
-// Restrictions of this draft: kchunk = 64 (Cin % 64 == 0), block_n in {128, 256}, one k-block per slot.
+// Restrictions: kchunk = 64 (Cin % 64 == 0), block_n in {128, 256}, one k-block per slot.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
 #include "conv_tc.cuh"
+#include "conv_epi.cuh"
 
 namespace cy4 {
 using namespace sm100;
@@ -219,6 +221,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                float g[32];
+                bool accum_in_store = (p.flags & CONV_F_ACCUM) != 0;
+                epi_transform(p, f, g, accum_in_store, n0, orow, row_ok);
                 if (p.flags & CONV_F_TMA_OUT) {
                     uint8_t *slab = (slab_i == 0 ? sOut : smem + kPRegion - slab_i * kPOutStage) + (warp - 2) * (32 * 64);
                     if (lane == 0) tma_store_wait_read_n(p.slab_bufs - 1);
@@ -256,7 +261,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
                         uint4 o; __half2 *ph = (__half2 *)&o;
-                        if (p.flags & CONV_F_ACCUM) {
+                        if (accum_in_store) {
                             const uint4 old = *(const uint4 *)(dst + i);
                             const __half2 *oh = (const __half2 *)&old;
 #pragma unroll
@@ -274,7 +279,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (p.flags & CONV_F_STATS) {
                     float s1[32], s2[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { s1[i] = f[i]; s2[i] = f[i] * f[i]; }
+                    for (int i = 0; i < 32; ++i) { s1[i] = f[i]; s2[i] = f[i] * (p.epi_mode == EPI_BWD_DZ ? g[i] : f[i]); }
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
                         const bool hi = (lane & off) != 0;

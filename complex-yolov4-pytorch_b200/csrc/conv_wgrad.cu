@@ -21,8 +21,6 @@
 namespace cy4 {
 using namespace sm100;
 extern int g_wgrad_cluster;      // conv_api.cu (cy4_set_option)
-extern int g_wgrad_variant;      // conv_api.cu: 2 routes cy4_conv_wgrad to the experimental persistent kernel (conv_wgrad2.cu)
-int conv_wgrad2_launch(const cy4_conv_desc *d, const void *x, const void *dy, float *dw_acc, void *stream);
 extern int g_debug;              // 1: skip the MMAs, 2: skip the TMA loads (bottleneck experiments only)
 
 // The TMA unit sustains roughly one bulk-tensor instruction per ~350 cycles per SM regardless of the
@@ -253,7 +251,6 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     const bool sw64 = d->Cin == 32;     // one [64 px x 32 ch] box, 64B swizzle: never reads past the 32 channels
     const int cin64 = sw64 ? 32 : (d->Cin + 63) / 64 * 64;
     CY4_CHECK_ARG(d->Cin % 32 == 0 && d->ldx >= (sw64 ? 32 : cin64) && d->ldx % 8 == 0, "cy4_conv_wgrad: x must be allocated with ld >= Cin rounded up to 64 (or Cin == 32)");
-    if (g_wgrad_variant == 2) return conv_wgrad2_launch(d, x, dy, dw_acc, stream);
     WgradParams p;
     memset(&p, 0, sizeof(p));
     wgrad_tiling(d, p);

@@ -13,8 +13,11 @@ def iou_matrix(boxes_wh_yaw, clusters_wh_yaw):
     """[n,3] x [k,3] (w, l, yaw; float64) -> float32 [n,k] on the device (find_anchors.py:53-59 for all boxes)."""
     _lib.require_device()
     L = _lib.lib()
-    b = torch.as_tensor(np.ascontiguousarray(boxes_wh_yaw, dtype=np.float64)).cuda().reshape(-1, 3)
-    c = torch.as_tensor(np.ascontiguousarray(clusters_wh_yaw, dtype=np.float64)).cuda().reshape(-1, 3)
+    def dev64(a):
+        if not torch.is_tensor(a):
+            a = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
+        return a.to("cuda", torch.float64).reshape(-1, 3).contiguous()
+    b, c = dev64(boxes_wh_yaw), dev64(clusters_wh_yaw)
     out = torch.empty(b.shape[0], c.shape[0], device=b.device, dtype=torch.float32)
     _lib.check(L.cy4_kmeans_iou(b.data_ptr(), b.shape[0], c.data_ptr(), c.shape[0], out.data_ptr(), _lib.stream()), "kmeans_iou")
     return out

@@ -178,8 +178,9 @@ class Darknet(nn.Module):
         self.engine_allreduce = False   # True (set by models.model_utils.make_data_parallel): the engine averages gradients over the ranks
                                         # itself, overlapped with backward; DDP then carries a no-op communication hook
         self.allreduce_groups = 6       # number of gradient groups of that exchange
-        self.fuse_bn_backward = 1       # 1: the dgrad epilogue of a tensor's last gradient writer does the producer's BN-backward reduce
-                                        # pass where its MMAs hide it (engine.Plan._plan_bwd_fusion); 2: wherever possible; 0: never
+        self.fuse_bn_backward = 0       # 0 (default): BN/activation backward as two bandwidth-bound passes.  1 / 2: the dgrad epilogue of a
+                                        # tensor's last gradient writer does the first pass (cy4_conv_dgrad_fused) on long-K layers / wherever
+                                        # possible -- measured SLOWER on B200 (profiles/r2_bn_backward_fusion.md), kept as a tested option
         self.fuse_eval = True           # eval() forward without grad: BatchNorm folded into the weights, activation in the conv epilogue
         self.outputs_on_device = False  # True: eval() forward returns the detections as a CUDA tensor (default: CPU, like the reference)
         self._engine = None

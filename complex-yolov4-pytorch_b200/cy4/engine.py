@@ -146,7 +146,7 @@ class StepEngine:
         # conv epilogue, no raw conv outputs kept
         infer = (not model.training) and not training_graph and bool(getattr(model, "fuse_eval", True))
         key = (tuple(x.shape), x.device, model.training, targets is not None,
-               tuple(p.data_ptr() for p in params[:4]), len(params), infer, int(getattr(model, "fuse_bn_backward", 1)))
+               tuple(p.data_ptr() for p in params[:4]), len(params), infer, int(getattr(model, "fuse_bn_backward", 0)))
         with torch.cuda.device(x.device):
             if self.key != key:
                 self.plan = None                          # release the old plan's buffers before allocating the new ones
@@ -159,7 +159,12 @@ class StepEngine:
                 out = self.plan.outputs()
                 if getattr(model, "outputs_on_device", False):
                     return out                            # device-resident: feed utils.evaluation_utils.post_processing_v2 directly
-                return out.to("cpu")                      # reference: to_cpu(torch.cat(yolo_outputs, 1))
+                # reference: to_cpu(torch.cat(yolo_outputs, 1)).  Through a pinned staging buffer (a pageable copy of the 29 MB
+                # tensor costs ~8 ms); a fresh CPU tensor is returned, the staging buffer is reused by the next call.
+                stage = self.plan.pinned_out(out)
+                stage.copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return stage.clone()
             if training_graph:
                 loss = _NetFn.apply(self, x, targets, *params)
             else:
@@ -530,7 +535,7 @@ class Plan:
         for st in cat_storage.values():
             self._storages.add(st)
 
-    def _plan_bwd_fusion(self):
+    def _plan_bwd_fusion(self, mode=None):
         """Static pass over the backward order: for every BatchNorm conv P whose activated output A receives its LAST
         gradient contribution from the input-gradient kernel of a conv C reading exactly that view, C's epilogue takes over
         the first pass of P's BN/activation backward (cy4_conv_dgrad_fused: dz = dA_total * act'(z) stored instead of dA,
@@ -539,7 +544,8 @@ class Plan:
         for rec in self.convs:
             rec["fuse_bwd"] = None          # consumer side: the producer rec whose reduce pass this conv's dgrad performs
             rec["reduce_fused"] = False     # producer side
-        mode = int(getattr(self.model, "fuse_bn_backward", 1))
+        if mode is None:
+            mode = int(getattr(self.model, "fuse_bn_backward", 0))
         if self.infer or not mode:
             return
         writers = {}                        # id(storage) -> [(lo, hi, kind, rec)] in backward order

@@ -163,36 +163,10 @@ def test_conv_wgrad(B, H, W, Cin, Cout, k, stride):
     assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("CY4_EXPERIMENTAL"),
-                    reason="experimental persistent wgrad kernel (conv_wgrad2.cu): written after the round's GPU budget was spent; "
-                           "set CY4_EXPERIMENTAL=1 to validate it")
-def test_conv_wgrad_persistent_variant():
-    """cy4_set_option("wgrad_variant", 2): same results as the default kernel up to the fp32 summation order, on the
-    parity cases plus a many-items-per-CTA shape."""
-    from cy4 import _lib, convops as co
-    L = _lib.lib()
-    for (B, H, W, Cin, Cout, k, stride) in WGRAD_CASES + [(8, 76, 76, 128, 128, 3, 1), (8, 152, 152, 32, 64, 3, 2)]:
-        torch.manual_seed(B + H + Cin)
-        pad = (k - 1) // 2
-        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-        x = torch.randn(B, H, W, Cin, device="cuda").half()
-        dy = (torch.randn(B, Ho, Wo, Cout, device="cuda") / (B * Ho * Wo) ** 0.5).half()
-        outs = []
-        for variant in (1, 2):
-            _lib.check(L.cy4_set_option(b"wgrad_variant", variant))
-            try:
-                outs.append(co.unpack_wgrad(co.conv_wgrad(x, dy, Cin, Cout, k, stride, pad), Cout, Cin, k))
-            finally:
-                _lib.check(L.cy4_set_option(b"wgrad_variant", 1))
-        assert (outs[0] - outs[1]).abs().max().item() <= 1e-3 * outs[0].abs().max().item() + 1e-5
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("CY4_EXPERIMENTAL"),
-                    reason="experimental CTA-pair conv kernel (conv_pair.cu): written after the round's GPU budget was spent; "
-                           "set CY4_EXPERIMENTAL=1 to validate it")
 def test_conv_pair_variant():
-    """cy4_set_option("conv_pair", 1): the cta_group::2 kernel against the default one (same K order: expect identical
-    fp16 outputs) and the fp32 reference, for fprop (+BN statistics), stride-1 / stride-2 dgrad, odd m-tile counts."""
+    """The CTA-pair (cta_group::2) kernel that serves every eligible launch by default against the 1-CTA kernel
+    (cy4_set_option("conv_pair", 0); same K order: identical fp16 outputs) and the fp32 reference, for fprop (+BN statistics),
+    stride-1 / stride-2 dgrad, odd m-tile counts."""
     from cy4 import _lib, convops as co
     L = _lib.lib()
     torch.manual_seed(77)
@@ -214,7 +188,7 @@ def test_conv_pair_variant():
                 torch.cuda.synchronize()
                 res.append((y.clone(), dx.clone(), s1.clone(), s2.clone()))
             finally:
-                _lib.check(L.cy4_set_option(b"conv_pair", 0))
+                _lib.check(L.cy4_set_option(b"conv_pair", 1))
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
         assert (res[0][2] - res[1][2]).abs().max().item() <= 1e-3 * res[0][2].abs().max().item() + 1e-3
         ref = _ref_conv(x, w, stride, pad)

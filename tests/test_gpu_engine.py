@@ -277,42 +277,37 @@ def test_fused_inference_vs_oracle_and_unfused(cfgname, size, B):
 @pytest.mark.parametrize("cfgname,size,B", [("complex_yolov4_tiny", 256, 2), ("complex_yolov4", 224, 2)])
 def test_fused_bn_backward_matches_separate_pass(cfgname, size, B):
     """cy4_conv_dgrad_fused (the first BN/activation-backward pass inside the input-gradient epilogue of the tensor's last
-    gradient writer) against the separate cy4_bn_act_bwd_reduce pass: same step, same weights, three engine configurations
-    (0 = never, 1 = where the MMAs hide it, 2 = wherever possible).  BatchNorm runs on its running statistics here: with batch
-    statistics the forward itself differs from run to run in the last bits of the atomically summed mean / variance, which a
-    randomly initialised 110-layer net amplifies to ~0.4 % of the loss (measured) -- more than the effect under test.  The fused
-    form computes dz from the fp32 accumulator instead of the fp16-rounded dA, so the gradients agree to fp16 rounding (and the
-    LeakyReLU kinks of the tiny cfg turn single-ulp differences into a little more)."""
+    gradient writer; optional, model.fuse_bn_backward = 1 | 2) against the default separate cy4_bn_act_bwd_reduce pass.
+    ONE training-mode forward, then the backward plan is run three times on that same forward state (retain_graph) with the
+    fusion flags of mode 0 / 1 / 2 -- so the comparison is free of the run-to-run differences of the atomically summed batch
+    statistics.  The fused form computes dz from the fp32 accumulator instead of the fp16-rounded dA: agreement to fp16 rounding."""
     from cy4 import netdefs, synth
     from cy4.darknet import Darknet
     strides = (16, 32) if "tiny" in cfgname else (8, 16, 32)
     x = synth.make_bev(B, img_size=size, seed=5).cuda()
     tg = torch.tensor(synth.make_targets(B, per_image=3, seed=2, img_size=size, strides=strides)).cuda()
-    grads, losses, nf = {}, {}, {}
+    torch.manual_seed(1)
+    model = Darknet(netdefs.cfg_path(cfgname), True).cuda().train()
+    model.fuse_bn_backward = 2
+    loss, _ = model(x, tg)
+    plan = model._engine.plan
+    grads, nf = {}, {}
     for mode in (0, 1, 2):
-        torch.manual_seed(1)
-        model = Darknet(netdefs.cfg_path(cfgname), True)
-        for m in model.modules():
-            if isinstance(m, torch.nn.BatchNorm2d):
-                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
-        model = model.cuda().eval()
-        model.fuse_bn_backward = mode
-        loss, _ = model(x, tg)
-        loss.backward()
+        plan._plan_bwd_fusion(mode)
+        nf[mode] = sum(1 for r in plan.convs if r["reduce_fused"])
+        model.zero_grad(set_to_none=True)
+        loss.backward(retain_graph=True)
         torch.cuda.synchronize()
-        nf[mode] = sum(1 for r in model._engine.plan.convs if r["reduce_fused"])
-        losses[mode] = loss.item()
         grads[mode] = {n: p.grad.clone() for n, p in model.named_parameters()}
     print(cfgname, "fused BN-backward layers per mode:", nf)
     assert nf[0] == 0 and nf[2] >= (5 if "tiny" in cfgname else 60) and 0 < nf[1] <= nf[2]
-    assert losses[0] == losses[1] == losses[2]                        # the forward pass is deterministic with running statistics
     for mode in (1, 2):
         worst = 1.0
         for n in grads[0]:
             c = _cos(grads[mode][n], grads[0][n])
             worst = min(worst, c)
             nr = abs(grads[mode][n].norm().item() - grads[0][n].norm().item()) / (grads[0][n].norm().item() + 1e-12)
-            assert c > 0.99 and nr < 0.02, (mode, n, c, nr)
+            assert c > 0.995 and nr < 0.02, (mode, n, c, nr)
         print("mode", mode, "worst cosine vs the separate pass", worst)
 
 

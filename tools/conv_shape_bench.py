@@ -49,20 +49,16 @@ for (Cin, Cout, k, s, H) in SHAPES:
     acc = torch.zeros((Cout + 31) // 32 * 32, k * k, Cin, device="cuda")
     fl = 2.0 * B * Ho * Ho * Cout * k * k * Cin
     rec = {"shape": [Cin, Cout, k, s, H], "count": COUNT.get((Cin, Cout, k, s, H), 1), "gflop": fl / 1e9}
-    for tag, opts in (("base", {}), ("pair", {b"conv_pair": 1})):
+    for tag, opts in (("base", {b"conv_pair": 0}), ("pair", {b"conv_pair": 1})):
         for o, v in opts.items():
             L.cy4_set_option(o, v)
         try:
             rec["fprop_" + tag] = timed(lambda: co.conv_fwd(x, wp, Cout, k, s, pad, out=y, stats=(s1, s2)))
             rec["dgrad_" + tag] = timed(lambda: co.conv_dgrad(dy[..., :Cout], wd, H, H, Cin, k, s, pad, out=dx))
         finally:
-            L.cy4_set_option(b"conv_pair", 0)
-    for tag, var in (("base", 1), ("persistent", 2)):
-        L.cy4_set_option(b"wgrad_variant", var)
-        try:
-            rec["wgrad_" + tag] = timed(lambda: co.conv_wgrad(x, dy, Cin, Cout, k, s, pad, acc=acc))
-        finally:
-            L.cy4_set_option(b"wgrad_variant", 1)
+            L.cy4_set_option(b"conv_pair", 1)
+    rec["wgrad_base"] = timed(lambda: co.conv_wgrad(x, dy, Cin, Cout, k, s, pad, acc=acc))
+    rec["wgrad_persistent"] = rec["wgrad_base"]          # (the persistent draft was measured slower everywhere in round 2 and removed)
     rows.append(rec)
     print("%-26s x%d  fprop %7.1f / pair %7.1f us (%6.0f TF/s) | dgrad %7.1f / pair %7.1f | wgrad %7.1f / persistent %7.1f" % (
         rec["shape"], rec["count"], rec["fprop_base"], rec["fprop_pair"], fl / min(rec["fprop_base"], rec["fprop_pair"]) / 1e6,
