@@ -95,7 +95,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 or args.force_ddp:
+        if world == 1:      # diagnostic: the DDP wrapper's host overhead without a second GPU
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     L = _lib.lib()
@@ -104,7 +107,7 @@ def run_ours(args):
     net = Darknet(netdefs.cfg_path(args.cfg), use_giou_loss=True).to(dev).train()
     net.use_cuda_graph = bool(args.cuda_graph)
     model = net
-    if world > 1:
+    if world > 1 or args.force_ddp:
         # unchanged PyTorch DDP (parameter broadcast, bucket views); the gradient all-reduce itself is issued by the engine in
         # groups while backward is still running (models/model_utils.py overlap_gradient_exchange), unless --ddp-stock
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=128)
@@ -129,10 +132,33 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        loss = step(x, tg)
-    sync()
+    graph_note = "off"
+    try:
+        for _ in range(args.warmup):
+            loss = step(x, tg)
+        sync()
+        if net.use_cuda_graph:
+            gs = net._engine.plan.graph_state
+            graph_note = "fwd+bwd launch sequences replayed as CUDA graphs" if (gs and gs.get("bwd") is not None) else "requested, not captured"
+    except Exception as e:      # noqa: BLE001 -- a failed capture must not cost the bench line: fall back to eager launches
+        if not net.use_cuda_graph:
+            raise
+        sys.stderr.write("bench: CUDA-graph capture failed (%r); falling back to eager launches\n" % (e,))
+        graph_note = "capture failed, eager launches"
+        net.use_cuda_graph = False
+        net._engine = None
+        torch.cuda.synchronize()
+        opt.zero_grad(set_to_none=True)
+        for _ in range(args.warmup):
+            loss = step(x, tg)
+        sync()
     assert torch.isfinite(loss).all(), "loss is not finite after warm-up: %r" % loss
+    # host time to ENQUEUE one step into an empty launch queue (no back-pressure): if this approaches ms_per_step the step is
+    # bound by the Python / ctypes launch path, not by the GPU
+    t_h = time.perf_counter()
+    loss = step(x, tg)
+    host_enqueue_ms = (time.perf_counter() - t_h) * 1e3
+    sync()
     # ---- timed region: K steps, inputs resident in HBM (the batch, weights and activations are far
     # larger than the 126 MB L2, so no explicit flush is needed between iterations)
     clocks = ClockSampler(local) if rank == 0 else None
@@ -333,10 +359,12 @@ def run_ours(args):
             "config": {"workload": workload_name(args.cfg, B),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "no flush needed: per-step working set (>20 GB) exceeds the 126 MB L2",
-                       "optimizer": "torch.optim.Adam(%s), reference parameter groups (train_utils.py:21-50)" % ("foreach" if args.adam_foreach else "fused=True")},
+                       "optimizer": "torch.optim.Adam(%s), reference parameter groups (train_utils.py:21-50)" % ("foreach" if args.adam_foreach else "fused=True"),
+                       "cuda_graph": graph_note},
             "e2e": {"value": round(world * B * args.steps / float(e2e_s.item()), 2), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "last_loss": lval},
             "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps,
+            "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
             "clocks": clk, "roofline": roof,
             "forward_only": None if not fwd_ms else {
                 "ms": round(fwd_ms, 3), "tflops": round(GFLOP_FWD_PER_IMG.get(args.cfg, 0) * B * 1e-3 / (fwd_ms / 1e3), 1),
@@ -349,8 +377,9 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_step_baseline(args.cfg, budget_s=25.0)
-    if world > 1:
-        dist.barrier()
+    if world > 1 or args.force_ddp:
+        if world > 1:
+            dist.barrier()
         dist.destroy_process_group()
     return result
 
@@ -534,10 +563,12 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--cfg", default="complex_yolov4")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
-    ap.add_argument("--cuda-graph", dest="cuda_graph", type=int, default=0, help="replay the fwd/bwd launch sequences as CUDA graphs")
+    ap.add_argument("--cuda-graph", dest="cuda_graph", type=int, default=1,
+                    help="1 (default): after two eager steps the fwd / bwd launch sequences (~850 kernels) are replayed as CUDA graphs; 0: eager launches")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT",
                     help="cy4_set_option(NAME, INT) before the run (kernel experiments, e.g. conv_cluster=2); recorded in config")
     ap.add_argument("--adam-foreach", dest="adam_foreach", action="store_true", help="torch.optim.Adam's default foreach path instead of fused=True")
+    ap.add_argument("--force-ddp", dest="force_ddp", action="store_true", help="wrap the model in DDP even with one rank (host-overhead diagnostic)")
     ap.add_argument("--ddp-stock", dest="ddp_stock", action="store_true",
                     help="N>1: let stock DDP do the (un-overlapped) bucketed all-reduce instead of the engine's overlapped exchange")
     ap.add_argument("--no-roofline", dest="no_roofline", action="store_true", help="skip the per-launch roofline pass (quick A/B runs)")

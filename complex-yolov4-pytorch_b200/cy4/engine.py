@@ -238,11 +238,18 @@ class StepEngine:
         if gs["bwd"] is None:
             gs["bwd"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gs["bwd"]):
-                gs["grads"] = plan.backward(gs["g"])
+                plan.backward(gs["g"])                   # (its return value -- copies made inside the capture -- is not used)
         gs["bwd"].replay()
-        # the captured gradient tensors are static graph memory: hand autograd private copies (it may keep what it gets
-        # as .grad, and the next replay overwrites the static buffers)
-        return [None if t is None else t.clone() for t in gs["grads"]]
+        # The gradient base tensors are static graph memory.  With the engine-side exchange (models.model_utils
+        # overlap_gradient_exchange: DDP carries a no-op hook) they are averaged over the ranks here, after the replay --
+        # not overlapped in this mode, but the ~850 launches of the step cost the host nothing, which is what bounds
+        # multi-rank steps (bench.py host_enqueue_ms_per_step).
+        if getattr(self.model, "engine_allreduce", False):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                for b in plan._grad_bases:
+                    dist.all_reduce(b, op=dist.ReduceOp.AVG)
+        return plan.materialise()
 
 
 class Plan:
@@ -832,7 +839,7 @@ class Plan:
         # gradient exchange done by the engine itself (model.engine_allreduce, set by models.model_utils.make_data_parallel
         # together with a no-op DDP communication hook): grouped, asynchronous, overlapped with the rest of backward
         ar_groups, works = None, []
-        if getattr(model, "engine_allreduce", False) and self.graph_state is None:
+        if getattr(model, "engine_allreduce", False) and (self.graph_state is None or self.graph_state["fwd"] is None):   # (eager steps)
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 ar_groups = self._allreduce_groups()
@@ -890,15 +897,30 @@ class Plan:
                     works.append(dist.all_reduce(gb, op=dist.ReduceOp.AVG, async_op=True))
             for w_ in works:
                 w_.wait()                                # the current stream waits for the exchange; the host does not block
-        fresh = gw_flat.clone()
+        # What autograd receives: views of a few BASE tensors (the flat conv-gradient buffer, the BN-gradient pair, the head
+        # biases).  `materialise` hands out views of private copies of the bases: AccumulateGrad keeps the tensors it is given
+        # as .grad, and the persistent / graph-static buffers are overwritten by the next backward.
+        bases, layout = [gw_flat, gbn], {}
         for w, off in self._wslices:
-            grads[id(w)] = fresh[off:off + w.numel()].view_as(w)
+            layout[id(w)] = (0, off, w.numel(), tuple(w.shape))
+        tc = gbn.shape[1]
         for rec in self.convs:
             if rec["bn"] is not None and rec.get("bn_bwd_done"):
                 c0, C = rec["coff"], rec["Cout"]
-                grads[id(rec["bn"].bias)] = gbn[0, c0:c0 + C]
-                grads[id(rec["bn"].weight)] = gbn[1, c0:c0 + C]
-        return [grads.get(id(p)) if p.requires_grad else None for p in self.params]
+                layout[id(rec["bn"].bias)] = (1, c0, C, (C,))
+                layout[id(rec["bn"].weight)] = (1, tc + c0, C, (C,))
+            b = rec["conv"].bias
+            if b is not None and id(b) in grads:
+                layout[id(b)] = (len(bases), 0, b.numel(), tuple(b.shape))
+                bases.append(grads[id(b)])
+        self._grad_bases = bases
+        self._grad_layout = [layout.get(id(p)) if p.requires_grad else None for p in self.params]
+        return self.materialise()
+
+    def materialise(self):
+        """Private copies of the gradient base tensors, re-sliced into one tensor per parameter (None where no gradient)."""
+        flats = [b.clone().reshape(-1) for b in self._grad_bases]
+        return [None if v is None else flats[v[0]][v[1]:v[1] + v[2]].view(v[3]) for v in self._grad_layout]
 
     def _allreduce_groups(self):
         """Gradient exchange plan: conv layers in backward order, cut into groups of roughly equal parameter

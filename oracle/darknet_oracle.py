@@ -120,7 +120,9 @@ def forward(blocks, sd, x, targets=None, use_giou=True, training=True, collect=N
             a = [float(i) for i in b["anchors"].split(",")]
             anchors = [(a[i], a[i + 1], math.sin(a[i + 2]), math.cos(a[i + 2])) for i in range(0, len(a), 3)]
             anchors = [anchors[i] for i in mask]
-            o, l, m, _ = yo.forward(x, targets, anchors, int(b["classes"]), img, float(b["ignore_thresh"]), use_giou)
+            # (the loss head restatement runs on the host: numpy + C geometry; the conv stack may be evaluated on any device)
+            o, l, m, _ = yo.forward(x.cpu() if x.is_cuda else x, targets.cpu() if (targets is not None and targets.is_cuda) else targets,
+                                    anchors, int(b["classes"]), img, float(b["ignore_thresh"]), use_giou)
             yolo_out.append(o)
             metrics.append(m)
             if targets is not None:
