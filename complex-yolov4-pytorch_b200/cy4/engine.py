@@ -598,6 +598,9 @@ class Plan:
             last = ws[-1]
             if last[2] != "conv" or last[3]["fuse_bwd"] is not None:
                 continue
+            if P["res"] is not None:
+                continue                    # A is a fused shortcut output: its RAW gradient is still needed by the residual branch
+                                            # (the [shortcut] event copies it after the last writer) -- dz must not replace it early
             # Mish' costs two MUFU operations per element and the eight epilogue warps are all the SM has for it while the
             # tile's MMAs run: 16 * N cycles per 128 x N tile.  The tensor work of that tile is k^2 * Cout / 64 k-blocks of
             # 2 * N cycles, so only input-gradient GEMMs with a long reduction (3 x 3, or very wide 1 x 1) hide the extra pass;

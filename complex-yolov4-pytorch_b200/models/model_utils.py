@@ -23,12 +23,13 @@ def get_num_parameters(model):
 
 def overlap_gradient_exchange(ddp_model):
     """The B200 engine exposes the whole network as one autograd node, so stock DDP would start its bucketed all-reduce only
-    after the last backward kernel.  Instead the engine averages the gradients itself while backward is still running
-    (cy4/engine.py: grouped asynchronous NCCL all-reduce, heavy layers first) and DDP keeps everything else it does
-    (parameter broadcast at construction, bucket views, no_sync bookkeeping) with a no-op communication hook."""
-    from torch.distributed.algorithms.ddp_comm_hooks.debugging_hooks import noop_hook
+    after the last backward kernel -- and it pays ~650 tiny copy / scale kernels per step to move the 327 freshly returned
+    gradient tensors into its buckets (+2 ms per step, measured with a single rank: profiles/r2_ddp_host_overhead.md).
+    Instead the engine averages the gradients itself while backward is still running (cy4/engine.py: grouped asynchronous NCCL
+    all-reduce, heavy layers first) and DDP keeps what else it does -- parameter broadcast at construction, buffer broadcast
+    every forward -- with its reducer switched off for good (the state `with ddp.no_sync():` sets for one block)."""
     ddp_model.module.engine_allreduce = True
-    ddp_model.register_comm_hook(None, noop_hook)
+    ddp_model.require_backward_grad_sync = False
     return ddp_model
 
 

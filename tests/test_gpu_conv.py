@@ -195,6 +195,33 @@ def test_conv_pair_variant():
         assert (res[1][0][..., :Cout].float().cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
 
 
+def test_conv_wgrad_pair_variant():
+    """cy4_set_option("wgrad_pair", 1): the CTA-pair (cta_group::2) weight-gradient kernel (Cout % 256 == 0, X tile of 128 / 256
+    channels) against the 1-CTA kernel (fp32 split-K atomics: summation order only) and autograd."""
+    from cy4 import _lib, convops as co
+    L = _lib.lib()
+    torch.manual_seed(41)
+    for (B, H, W, Cin, Cout, k, stride) in [(2, 38, 38, 256, 512, 3, 1), (3, 19, 19, 512, 256, 1, 1), (4, 19, 19, 512, 1024, 3, 1),
+                                            (2, 76, 76, 128, 256, 3, 2), (2, 38, 38, 128, 256, 3, 1), (32, 38, 38, 256, 512, 3, 1)]:
+        pad = (k - 1) // 2
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        x = torch.randn(B, H, W, Cin, device="cuda").half()
+        dy = (torch.randn(B, Ho, Wo, Cout, device="cuda") / (B * Ho * Wo) ** 0.5).half()
+        outs = []
+        for pair in (0, 1):
+            _lib.check(L.cy4_set_option(b"wgrad_pair", pair))
+            try:
+                outs.append(co.unpack_wgrad(co.conv_wgrad(x, dy, Cin, Cout, k, stride, pad), Cout, Cin, k))
+                torch.cuda.synchronize()
+            finally:
+                _lib.check(L.cy4_set_option(b"wgrad_pair", 0))
+        assert (outs[0] - outs[1]).abs().max().item() <= 1e-3 * outs[0].abs().max().item() + 1e-6, (B, H, Cin, Cout, k, stride)
+        if B <= 4:
+            w = torch.zeros(Cout, Cin, k, k, requires_grad=True)
+            F.conv2d(x.float().cpu().permute(0, 3, 1, 2), w, None, stride, pad).backward(dy.float().cpu().permute(0, 3, 1, 2))
+            assert (outs[1].cpu() - w.grad).abs().max().item() <= 2e-3 * w.grad.abs().max().item() + 1e-4
+
+
 def test_conv_wgrad_stem_and_narrow():
     """Stem cols matrix (32 wide, 64B-swizzle B operand) and 32-channel tensors stored with ld=64."""
     from cy4 import convops as co

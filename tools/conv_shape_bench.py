@@ -57,14 +57,18 @@ for (Cin, Cout, k, s, H) in SHAPES:
             rec["dgrad_" + tag] = timed(lambda: co.conv_dgrad(dy[..., :Cout], wd, H, H, Cin, k, s, pad, out=dx))
         finally:
             L.cy4_set_option(b"conv_pair", 1)
-    rec["wgrad_base"] = timed(lambda: co.conv_wgrad(x, dy, Cin, Cout, k, s, pad, acc=acc))
-    rec["wgrad_persistent"] = rec["wgrad_base"]          # (the persistent draft was measured slower everywhere in round 2 and removed)
+    for tag, var in (("base", 0), ("persistent", 1)):      # ("persistent" column = wgrad_pair: the cta_group::2 weight-gradient kernel)
+        L.cy4_set_option(b"wgrad_pair", var)
+        try:
+            rec["wgrad_" + tag] = timed(lambda: co.conv_wgrad(x, dy, Cin, Cout, k, s, pad, acc=acc))
+        finally:
+            L.cy4_set_option(b"wgrad_pair", 0)
     rows.append(rec)
-    print("%-26s x%d  fprop %7.1f / pair %7.1f us (%6.0f TF/s) | dgrad %7.1f / pair %7.1f | wgrad %7.1f / persistent %7.1f" % (
+    print("%-26s x%d  fprop %7.1f / pair %7.1f us (%6.0f TF/s) | dgrad %7.1f / pair %7.1f | wgrad %7.1f / pair %7.1f" % (
         rec["shape"], rec["count"], rec["fprop_base"], rec["fprop_pair"], fl / min(rec["fprop_base"], rec["fprop_pair"]) / 1e6,
         rec["dgrad_base"], rec["dgrad_pair"], rec["wgrad_base"], rec["wgrad_persistent"]), flush=True)
 tot = lambda key: sum(r[key] * r["count"] for r in rows) / 1e3
-print("step totals (ms): fprop base %.3f pair %.3f best %.3f | dgrad base %.3f pair %.3f best %.3f | wgrad base %.3f persistent %.3f best %.3f" % (
+print("step totals (ms): fprop base %.3f pair %.3f best %.3f | dgrad base %.3f pair %.3f best %.3f | wgrad base %.3f pair %.3f best %.3f" % (
     tot("fprop_base"), tot("fprop_pair"), sum(min(r["fprop_base"], r["fprop_pair"]) * r["count"] for r in rows) / 1e3,
     tot("dgrad_base"), tot("dgrad_pair"), sum(min(r["dgrad_base"], r["dgrad_pair"]) * r["count"] for r in rows) / 1e3,
     tot("wgrad_base"), tot("wgrad_persistent"), sum(min(r["wgrad_base"], r["wgrad_persistent"]) * r["count"] for r in rows) / 1e3))
