@@ -288,7 +288,7 @@ def run_ours(args):
                     fwd_ms = fa.elapsed_time(fb) / 5
             except Exception as e:      # noqa: BLE001
                 sys.stderr.write("forward-only timing failed: %r\n" % (e,))
-            roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fprop launches)", "achieved": round(achieved, 1), "peak": pk["tf_sustained"],
+            roof = {"bound": "tensor", "kernel": "conv fprop launches (conv_pair_kernel, conv_tc_kernel for the shapes the pair kernel does not take)", "achieved": round(achieved, 1), "peak": pk["tf_sustained"],
                     "unit": "TFLOP/s", "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": pk["src"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
                     "flops_per_step": fwd[1] / 2, "avg_launch_ms": fwd[0] / max(fwd[2], 1), "by_kernel": tc,

@@ -45,6 +45,14 @@ long long cy4_kernel_launches(int reset)
     return reset ? cy4::g_launches.exchange(0) : cy4::g_launches.load();
 }
 
+/* A CUDA graph replay launches the kernels that were captured into it without passing through the entry points that count:
+ * the caller reports them (n = number of this library's kernel nodes in the replayed graph). */
+int cy4_note_graph_replay(int n_kernels)
+{
+    if (n_kernels > 0) cy4::g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
+    return 0;
+}
+
 int cy4_device_ok(void)
 {
     int n = 0;

@@ -25,7 +25,7 @@ int g_debug = 0;
 int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disables the packing)
 int g_conv_pair = 1;        // CTA-pair (cta_group::2) conv kernel for the eligible launches (conv_pair.cu); 0: always the 1-CTA kernel
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
-int g_wgrad_pair = 0;       // 1: CTA-pair weight-gradient kernel for the eligible launches (conv_wgrad.cu conv_wgrad_pair_kernel)
+int g_wgrad_pair = 1;       // CTA-pair weight-gradient kernel for the eligible launches (conv_wgrad.cu conv_wgrad_pair_kernel)
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.

@@ -36,6 +36,7 @@ _SIGS = {
     "cy4_last_error": (ctypes.c_char_p, []),
     "cy4_device_ok": (ctypes.c_int, []),
     "cy4_kernel_launches": (ctypes.c_longlong, [ctypes.c_int]),
+    "cy4_note_graph_replay": (ctypes.c_int, [ctypes.c_int]),
     "cy4_rgiou_pairs": (ctypes.c_int, [c_f, c_f, c_i64, c_u32, c_f, c_f, c_f, c_f, c_vp]),
     "cy4_sum_f32_seq": (ctypes.c_int, [c_f, c_i64, c_f, c_vp]),
     "cy4_corners": (ctypes.c_int, [c_f, c_f, c_f, c_f, c_f, c_i64, c_f, c_vp]),

@@ -219,11 +219,14 @@ class StepEngine:
         gs["tg"].copy_(targets)
         if gs["fwd"] is None:
             plan.force_pack = True
+            n0 = int(self.L.cy4_kernel_launches(0))
             gs["fwd"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gs["fwd"]):
                 gs["loss"] = plan.forward(gs["x"], gs["tg"], model.use_giou_loss)
+            gs["fwd_launches"] = int(self.L.cy4_kernel_launches(0)) - n0      # kernel nodes of this library in the graph
             plan.force_pack = False
         gs["fwd"].replay()
+        self.L.cy4_note_graph_replay(gs["fwd_launches"])
         for y in plan.yolos:
             y["layer"].metrics = LazyMetrics(y["metrics_out"])
         return gs["loss"].clone()
@@ -236,10 +239,13 @@ class StepEngine:
             return plan.backward(gloss)
         gs["g"].copy_(gloss.reshape(-1)[:1])
         if gs["bwd"] is None:
+            n0 = int(self.L.cy4_kernel_launches(0))
             gs["bwd"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gs["bwd"]):
                 plan.backward(gs["g"])                   # (its return value -- copies made inside the capture -- is not used)
+            gs["bwd_launches"] = int(self.L.cy4_kernel_launches(0)) - n0
         gs["bwd"].replay()
+        self.L.cy4_note_graph_replay(gs["bwd_launches"])
         # The gradient base tensors are static graph memory.  With the engine-side exchange (models.model_utils
         # overlap_gradient_exchange: DDP carries a no-op hook) they are averaged over the ranks here, after the replay --
         # not overlapped in this mode, but the ~850 launches of the step cost the host nothing, which is what bounds

@@ -42,6 +42,9 @@ CY4_API const char *cy4_last_error(void);
 CY4_API int cy4_device_ok(void);
 /* number of CUDA kernels this library has launched in this process (reset != 0: return and clear) */
 CY4_API long long cy4_kernel_launches(int reset);
+/* Kernels launched by replaying a CUDA graph do not pass through the counting entry points: after each replay the caller adds
+ * the number of this library's kernel launches that were captured into that graph (cy4_kernel_launches delta over the capture). */
+CY4_API int cy4_note_graph_replay(int n_kernels);
 
 /* ---- rotated-box geometry -------------------------------------------------------------------
  * utils/iou_rotated_boxes_utils.py:98-142  iou_pred_vs_target_boxes (element-wise pairs), with
@@ -148,7 +151,7 @@ typedef struct cy4_conv_desc {
  * slabs through TMA multicast; "tma_store" (0|1): swizzled-smem + TMA-store epilogue of the fp16 outputs;
  * "kblocks_per_slot" (1..8, default 4): upper bound on the k-blocks of a narrow layer packed into one pipeline slot;
  * "conv1x1_matrix" (0|1): 1 = 1x1 / stride-1 convs read their activation through a plain 2-D tiled TMA instead of im2col mode;
- * "wgrad_pair" (0|1): CTA-pair weight-gradient kernel for layers with Cout % 256 == 0 and a 128/256-channel X tile;
+ * "wgrad_pair" (0|1, default 1): CTA-pair weight-gradient kernel for layers with Cout % 256 == 0 and a 128/256-channel X tile;
  * "conv_pair" (0|1, default 1): CTA-pair (tcgen05 cta_group::2, 256-row tiles) kernel for the eligible conv launches;
  * "debug": bottleneck experiments, honoured only by -DCY4_PROBE side builds (tools/probe_pipeline.py). */
 CY4_API int cy4_set_option(const char *name, int value);

@@ -196,8 +196,9 @@ def test_conv_pair_variant():
 
 
 def test_conv_wgrad_pair_variant():
-    """cy4_set_option("wgrad_pair", 1): the CTA-pair (cta_group::2) weight-gradient kernel (Cout % 256 == 0, X tile of 128 / 256
-    channels) against the 1-CTA kernel (fp32 split-K atomics: summation order only) and autograd."""
+    """The CTA-pair (cta_group::2) weight-gradient kernel that serves the eligible launches by default (Cout % 256 == 0, X tile
+    of 128 / 256 channels) against the 1-CTA kernel (cy4_set_option("wgrad_pair", 0); fp32 split-K atomics: summation order
+    only) and autograd."""
     from cy4 import _lib, convops as co
     L = _lib.lib()
     torch.manual_seed(41)
@@ -214,7 +215,7 @@ def test_conv_wgrad_pair_variant():
                 outs.append(co.unpack_wgrad(co.conv_wgrad(x, dy, Cin, Cout, k, stride, pad), Cout, Cin, k))
                 torch.cuda.synchronize()
             finally:
-                _lib.check(L.cy4_set_option(b"wgrad_pair", 0))
+                _lib.check(L.cy4_set_option(b"wgrad_pair", 1))
         assert (outs[0] - outs[1]).abs().max().item() <= 1e-3 * outs[0].abs().max().item() + 1e-6, (B, H, Cin, Cout, k, stride)
         if B <= 4:
             w = torch.zeros(Cout, Cin, k, k, requires_grad=True)

@@ -62,7 +62,7 @@ for (Cin, Cout, k, s, H) in SHAPES:
         try:
             rec["wgrad_" + tag] = timed(lambda: co.conv_wgrad(x, dy, Cin, Cout, k, s, pad, acc=acc))
         finally:
-            L.cy4_set_option(b"wgrad_pair", 0)
+            L.cy4_set_option(b"wgrad_pair", 1)
     rows.append(rec)
     print("%-26s x%d  fprop %7.1f / pair %7.1f us (%6.0f TF/s) | dgrad %7.1f / pair %7.1f | wgrad %7.1f / pair %7.1f" % (
         rec["shape"], rec["count"], rec["fprop_base"], rec["fprop_pair"], fl / min(rec["fprop_base"], rec["fprop_pair"]) / 1e6,
