@@ -199,27 +199,33 @@ def run_ours(args):
     # after a per-step host synchronisation; the last step's results are read inside the timed region.
     loss_host = torch.zeros(2, 1, pin_memory=True)
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_loop(n):
+        nxt = h2d()
+        lv, out_ = None, None
+        for i in range(n):
+            xd, td, ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            xd.record_stream(torch.cuda.current_stream()); td.record_stream(torch.cuda.current_stream())
+            loss_, out_ = model(xd, td)
+            loss_.backward()
+            if i + 1 < n:
+                nxt = h2d()                  # every step copies its own batch from the host, one step ahead
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            loss_host[i & 1].copy_(loss_.detach().reshape(1), non_blocking=True)     # device -> host read of the step's result
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                lv = float(loss_host[(i - 1) & 1])
+        loss_ev[(n - 1) & 1].synchronize()
+        lv = float(loss_host[(n - 1) & 1])
+        return lv, out_
+
+    e2e_loop(2)                              # untimed: first-use allocations of the per-step input tensors / pinned staging
     sync()
     t0 = time.perf_counter()
-    nxt = h2d()
-    lval = None
-    for i in range(args.steps):
-        xd, td, ev = nxt
-        torch.cuda.current_stream().wait_event(ev)
-        xd.record_stream(torch.cuda.current_stream()); td.record_stream(torch.cuda.current_stream())
-        loss, out = model(xd, td)
-        loss.backward()
-        if i + 1 < args.steps:
-            nxt = h2d()                      # every step copies its own batch from the host, one step ahead
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        loss_host[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)     # device -> host read of the step's result
-        loss_ev[i & 1].record()
-        if i > 0:
-            loss_ev[(i - 1) & 1].synchronize()
-            lval = float(loss_host[(i - 1) & 1])
-    loss_ev[(args.steps - 1) & 1].synchronize()
-    lval = float(loss_host[(args.steps - 1) & 1])
+    lval, out = e2e_loop(args.steps)
     sync()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:

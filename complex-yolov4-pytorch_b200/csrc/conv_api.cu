@@ -206,29 +206,28 @@ pack_batched_kernel(const cy4_pack_item *__restrict__ items, int n)
         __half *of = (__half *)it.w_fprop, *od = (__half *)it.w_dgrad;
         const int tile = gt - it.tile_begin;
         const int co0 = (tile / tiles_ci) * kPkT, ci0 = (tile % tiles_ci) * kPkT;
-        for (int i = threadIdx.x; i < kPkT * run; i += 256) {
-            const int r = i / run, c = i - r * run;       // c = ci_local * kk + tap
-            const int co = co0 + r, ci = ci0 + c / kk;
-            t[r][c] = (co < Cout && ci < Cin) ? w[(int64_t)co * Cin * kk + (int64_t)ci0 * kk + c] : 0.f;
+        // (index arithmetic without divisions: a warp owns whole rows, lanes run along the contiguous dimension; Cin is a
+        // multiple of 32, so a ci tile is always full)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < kPkT; r += 8) {
+            const int co = co0 + r;
+            const float *src = w + (int64_t)co * Cin * kk + (int64_t)ci0 * kk;
+            for (int c = lane; c < run; c += 32) t[r][c] = co < Cout ? src[c] : 0.f;
         }
         __syncthreads();
         if (of) {                                         // [cout_pad][tap][Cin]
-            for (int i = threadIdx.x; i < kPkT * run; i += 256) {
-                const int r = i / run, rem = i - r * run;
-                const int tap = rem / kPkT, ci = rem - tap * kPkT;
+            for (int r = warp; r < kPkT; r += 8) {
                 const int co = co0 + r;
-                if (co < it.cout_pad && ci0 + ci < Cin)
-                    of[((int64_t)co * kk + tap) * Cin + ci0 + ci] =
-                        __float2half_rn(t[r][ci * kk + tap] * ((it.fold_scale && co < Cout) ? __ldg(it.fold_scale + co) : 1.f));
+                if (co >= it.cout_pad) break;
+                const float fs = (it.fold_scale && co < Cout) ? __ldg(it.fold_scale + co) : 1.f;
+                for (int tap = 0; tap < kk; ++tap)
+                    of[((int64_t)co * kk + tap) * Cin + ci0 + lane] = __float2half_rn(t[r][lane * kk + tap] * fs);
             }
         }
-        if (od) {                                         // [cin_pad][tap][cout_pad]
-            for (int i = threadIdx.x; i < kPkT * run; i += 256) {
-                const int cil = i / run, rem = i - cil * run;
-                const int tap = rem / kPkT, col = rem - tap * kPkT;
-                if (ci0 + cil < it.cin_pad && co0 + col < it.cout_pad)
-                    od[((int64_t)(ci0 + cil) * kk + tap) * it.cout_pad + co0 + col] = __float2half_rn(t[col][cil * kk + tap]);
-            }
+        if (od && co0 + lane < it.cout_pad) {             // [cin_pad][tap][cout_pad]
+            for (int cil = warp; cil < kPkT; cil += 8)
+                for (int tap = 0; tap < kk; ++tap)
+                    od[((int64_t)(ci0 + cil) * kk + tap) * it.cout_pad + co0 + lane] = __float2half_rn(t[lane][cil * kk + tap]);
         }
         __syncthreads();
     }
@@ -248,17 +247,18 @@ unpack_batched_kernel(const cy4_unpack_item *__restrict__ items, int n, const fl
         const int tiles_ci = (Cin + kPkT - 1) / kPkT;
         const int tile = gt - it.tile_begin;
         const int co0 = (tile / tiles_ci) * kPkT, ci0 = (tile % tiles_ci) * kPkT;
-        for (int i = threadIdx.x; i < kPkT * run; i += 256) {       // read acc[co][tap][ci0 .. ci0+32): 32 contiguous floats
-            const int r = i / run, rem = i - r * run;
-            const int tap = rem / kPkT, ci = rem - tap * kPkT;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < kPkT; r += 8) {                      // read acc[co][tap][ci0 .. ci0+32): 32 contiguous floats
             const int co = co0 + r;
-            t[r][ci * kk + tap] = (co < Cout && ci0 + ci < Cin) ? it.dw_acc[((int64_t)co * kk + tap) * Cin + ci0 + ci] : 0.f;
+            for (int tap = 0; tap < kk; ++tap)
+                t[r][lane * kk + tap] = co < Cout ? it.dw_acc[((int64_t)co * kk + tap) * Cin + ci0 + lane] : 0.f;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < kPkT * run; i += 256) {       // write gw[co][ci0*kk .. (ci0+32)*kk): one contiguous run
-            const int r = i / run, c = i - r * run;
+        for (int r = warp; r < kPkT; r += 8) {                      // write gw[co][ci0*kk .. (ci0+32)*kk): one contiguous run
             const int co = co0 + r;
-            if (co < Cout && ci0 + c / kk < Cin) it.gw_oihw[(int64_t)co * Cin * kk + (int64_t)ci0 * kk + c] = scale * t[r][c];
+            if (co >= Cout) break;
+            float *dst = it.gw_oihw + (int64_t)co * Cin * kk + (int64_t)ci0 * kk;
+            for (int c = lane; c < run; c += 32) dst[c] = scale * t[r][c];
         }
         __syncthreads();
     }
