@@ -102,6 +102,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     L = _lib.lib()
+    for o in args.opt:                       # kernel experiments: cy4_set_option(NAME, INT)
+        name, val = o.split("=")
+        _lib.check(L.cy4_set_option(name.encode(), int(val)), "cy4_set_option(%s)" % o)
     B = args.batch
     torch.manual_seed(0)
     net = Darknet(netdefs.cfg_path(args.cfg), use_giou_loss=True).to(dev).train()
@@ -366,7 +369,7 @@ def run_ours(args):
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "no flush needed: per-step working set (>20 GB) exceeds the 126 MB L2",
                        "optimizer": "torch.optim.Adam(%s), reference parameter groups (train_utils.py:21-50)" % ("foreach" if args.adam_foreach else "fused=True"),
-                       "cuda_graph": graph_note},
+                       "cuda_graph": graph_note, **({"options": args.opt} if args.opt else {})},
             "e2e": {"value": round(world * B * args.steps / float(e2e_s.item()), 2), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "last_loss": lval},
             "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps,

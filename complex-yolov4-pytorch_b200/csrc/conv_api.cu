@@ -26,6 +26,7 @@ int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disable
 int g_conv_pair = 1;        // CTA-pair (cta_group::2) conv kernel for the eligible launches (conv_pair.cu); 0: always the 1-CTA kernel
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 int g_wgrad_pair = 1;       // CTA-pair weight-gradient kernel for the eligible launches (conv_wgrad.cu conv_wgrad_pair_kernel)
+int g_accum_tma = 1;        // accumulate-mode outputs through TMA reduce-add stores (0: per-thread read-modify-write)
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
@@ -41,6 +42,7 @@ struct GenericConv {
     const float *bias; float *ch_sum, *ch_sqsum;
     int a_matrix;
     int epi_mode, epi_act; const float *epi_scale, *epi_shift; const void *side; int64_t ld_side;   // fused epilogue (conv_tc.cuh)
+    int ncls; uint8_t cls_tap0[4], cls_ntap[4], cls_oh0[4], cls_ow0[4];                              // tap classes merged into one launch
 };
 
 static int run_generic(const GenericConv &g, cudaStream_t st)
@@ -66,6 +68,12 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     p.bias = g.bias; p.ch_sum = g.ch_sum; p.ch_sqsum = g.ch_sqsum;
     p.epi_mode = g.epi_mode; p.epi_act = g.epi_act; p.epi_scale = g.epi_scale; p.epi_shift = g.epi_shift;
     p.side = g.side; p.ld_side = g.ld_side;
+    p.ncls = g.ncls;
+    int min_taps = g.ntaps;
+    for (int c = 0; c < g.ncls && c < 4; ++c) {
+        p.cls_tap0[c] = g.cls_tap0[c]; p.cls_ntap[c] = g.cls_ntap[c]; p.cls_oh0[c] = g.cls_oh0[c]; p.cls_ow0[c] = g.cls_ow0[c];
+        min_taps = std::min(min_taps, (int)g.cls_ntap[c]);
+    }
     if (p.M <= 0) return 0;
     const int swz = p.kchunk * 2;
     alignas(64) CUtensorMap tmA, tmB;
@@ -92,11 +100,15 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     // Every slot costs the issue threads a barrier round trip and a commit (~250 cycles, tools/probe_pipeline.py),
     // more than the MMAs of one narrow k-block (128 cycles at N = 64): pack several k-blocks per slot while a
     // slot stays <= 48 KB.
-    const int num_kb = g.ntaps * p.cin_chunks;
+    const int num_kb = min_taps * p.cin_chunks;          // (of the shortest tap class)
     p.kps = (p.cluster == 1 && g_kps_max > 1) ? std::max(1, std::min(std::min(g_kps_max, num_kb), 49152 / (p.a_stage + p.b_stage))) : 1;
     p.stages = std::max(2, std::min(12, (4 * 49152 - slab_extra) / (p.kps * (p.a_stage + p.b_stage))));
     alignas(64) CUtensorMap tmC = tmB;
-    if (!(p.flags & (CONV_F_OUT_F32 | CONV_F_ACCUM)) && !p.omap && !g_disable_tma_out) {
+    // Accumulating launches (y += result: gradients of tensors with several consumers) keep the slab path too: the slab is
+    // ADDED to global memory by a TMA reduce (cp.reduce.async.bulk.tensor ... .add, fp16) instead of a per-thread strided
+    // read-modify-write.  Not for EPI_BWD_DZ, which needs the total in registers before it applies act'.
+    const bool accum_tma = (p.flags & CONV_F_ACCUM) && p.epi_mode != EPI_BWD_DZ && g_accum_tma;
+    if (!(p.flags & CONV_F_OUT_F32) && (!(p.flags & CONV_F_ACCUM) || accum_tma) && !p.omap && !g_disable_tma_out) {
         // dense fp16 output: epilogue stages 32-row slabs in swizzled smem and TMA-stores them
         const int cw = 32;
         rc = make_tmap_2d(&tmC, g.y, (uint64_t)g.w_rows_pad, (uint64_t)p.M, (uint64_t)g.ldy * 2, cw, 32, cw * 2, 0);
@@ -342,6 +354,7 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
     if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
     if (!strcmp(name, "kblocks_per_slot")) { g_kps_max = value < 1 ? 1 : (value > 8 ? 8 : value); return 0; }
+    if (!strcmp(name, "accum_tma")) { g_accum_tma = value ? 1 : 0; return 0; }
     if (!strcmp(name, "wgrad_pair")) { g_wgrad_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv1x1_matrix")) { g_conv1x1_matrix = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv_pair")) { g_conv_pair = value ? 1 : 0; return 0; }
@@ -461,23 +474,25 @@ static int conv_dgrad_impl(const cy4_conv_desc *d, const void *dy, const void *w
     g.lower_w = g.lower_h = 0; g.upper_w = g.upper_h = 0; g.tstride = 1;
     g.Po = d->Hi / 2; g.Qo = d->Wi / 2;
     g.omap = 1; g.OH = d->Hi; g.OW = d->Wi; g.ostep = 2;
+    // All four parity classes in ONE launch (work unit -> class): a single grid instead of four part-filled ones.
     static const int cls_n[2] = {1, 2};
     static const int cls_r[2][2] = {{1, 0}, {0, 2}};
     static const int cls_o[2][2] = {{0, 0}, {1, 0}};
+    g.ntaps = 0; g.ncls = 0;
     for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
-            g.oh0 = ph; g.ow0 = pw;
-            g.ntaps = 0;
+            const int c = g.ncls++;
+            g.cls_oh0[c] = (uint8_t)ph; g.cls_ow0[c] = (uint8_t)pw;
+            g.cls_tap0[c] = (uint8_t)g.ntaps;
             for (int a = 0; a < cls_n[ph]; ++a)
                 for (int b = 0; b < cls_n[pw]; ++b) {
                     const int t = g.ntaps++;
                     g.oh[t] = (uint8_t)cls_o[ph][a]; g.ow[t] = (uint8_t)cls_o[pw][b];
                     g.kofs[t] = (cls_r[ph][a] * 3 + cls_r[pw][b]) * d->Cout;
                 }
-            const int rc = run_generic(g, (cudaStream_t)stream);
-            if (rc) return rc;
+            g.cls_ntap[c] = (uint8_t)(g.ntaps - g.cls_tap0[c]);
         }
-    return 0;
+    return run_generic(g, (cudaStream_t)stream);
 }
 
 int cy4_pack_weight_fprop(const float *w_oihw, int Cout, int Cin, int ksize, int cin_pad, void *w_packed, void *stream)

@@ -65,8 +65,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int crank = (int)cluster_ctarank();                   // 0 = leader (issues the MMAs), 1 = peer
     const int unit0 = (int)cluster_id_x(), unit_step = (int)ncluster_x();
-    const int units = ((p.tiles_m + 1) / 2) * p.tiles_n;        // pairs of m tiles x n tiles
-    const int num_kb = p.ntaps * p.cin_chunks;
+    const int cls_units = ((p.tiles_m + 1) / 2) * p.tiles_n;    // pairs of m tiles x n tiles (of one tap class)
+    const int ncls = p.ncls > 1 ? p.ncls : 1;
+    const int units = cls_units * ncls;
     const int half_n = p.block_n / 2;
     const uint32_t a_bytes = kPM * 64 * 2, b_half_bytes = (uint32_t)half_n * 64 * 2;
 
@@ -90,13 +91,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int t = unit0; t < units; t += unit_step) {
-                const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * 2 + crank;
+                const int cls = t / cls_units, tt = t - cls * cls_units;
+                const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
+                const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * 2 + crank;
                 const int m0 = m_blk * kPM;
                 const int img = m0 / (p.Po * p.Qo);
                 const int rem = m0 - img * (p.Po * p.Qo);
                 const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
                 const int bw = qi * p.tstride + p.lower_w, bh = pi * p.tstride + p.lower_h;
-                int tap = 0, cc = 0;
+                int tap = ncls > 1 ? p.cls_tap0[cls] : 0, cc = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&ctl->empty[stage], phase ^ 1);                  // my own slot was consumed (multicast commit)
                     if (crank == 0) mbar_expect_tx(&ctl->full[stage], 2 * (a_bytes + b_half_bytes));   // bytes of BOTH CTAs
@@ -124,6 +127,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);         // both CTAs' epilogues have drained this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.block_n;
+                const int num_kb = (ncls > 1 ? p.cls_ntap[t / cls_units] : p.ntaps) * p.cin_chunks;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&ctl->full[stage], phase);
                     tc_fence_after();
@@ -150,7 +154,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int slab_i = 0;
         for (int t = unit0; t < units; t += unit_step, ++seq) {
             if ((seq & 1) != group) continue;
-            const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * 2 + crank;
+            const int cls = t / cls_units, tt = t - cls * cls_units;
+            const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * 2 + crank;
             const int m = m_blk * kPM + quarter * 32 + lane;
             const bool row_ok = m < p.M;
             int64_t orow = m;
@@ -158,7 +163,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int img = m / (p.Po * p.Qo);
                 const int rem = m - img * (p.Po * p.Qo);
                 const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
-                orow = ((int64_t)img * p.OH + (pi * p.ostep + p.oh0)) * p.OW + (qi * p.ostep + p.ow0);
+                const int oh0 = ncls > 1 ? p.cls_oh0[cls] : p.oh0, ow0 = ncls > 1 ? p.cls_ow0[cls] : p.ow0;
+                orow = ((int64_t)img * p.OH + (pi * p.ostep + oh0)) * p.OW + (qi * p.ostep + ow0);
             }
             mbar_wait(&ctl->tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -190,7 +196,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tmC, slab, n_blk * p.block_n + c * 32, m_blk * kPM + quarter * 32);
+                        if (p.flags & CONV_F_ACCUM) tma_reduce_add_2d(&tmC, slab, n_blk * p.block_n + c * 32, m_blk * kPM + quarter * 32);
+                        else tma_store_2d(&tmC, slab, n_blk * p.block_n + c * 32, m_blk * kPM + quarter * 32);
                         tma_store_commit();
                     }
                 } else if (p.flags & CONV_F_OUT_F32) {
@@ -290,7 +297,7 @@ int launch_conv_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUten
     p.a_stage = kPM * 64 * 2;                                    // 16 KB
     p.b_stage = (p.block_n / 2) * 64 * 2;                        // 16 KB (N = 256) or 8 KB (N = 128): this CTA's half
     p.stages = std::max(2, std::min(kPMaxStages, (kPRegion - (p.slab_bufs - 1) * kPOutStage) / (p.a_stage + p.b_stage)));
-    const int units = ((p.tiles_m + 1) / 2) * p.tiles_n;
+    const int units = ((p.tiles_m + 1) / 2) * p.tiles_n * (p.ncls > 1 ? p.ncls : 1);
     const int grid = std::min(units, sm_count() / 2) * 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -106,9 +106,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
     const int unit0 = cs > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
     const int unit_step = cs > 1 ? (int)ncluster_x() : (int)gridDim.x;
-    const int units = ((p.tiles_m + cs - 1) / cs) * p.tiles_n;
+    const int cls_units = ((p.tiles_m + cs - 1) / cs) * p.tiles_n;          // units of one tap class
+    const int ncls = p.ncls > 1 ? p.ncls : 1;
+    const int units = cls_units * ncls;
     const uint16_t cmask = (uint16_t)((1u << cs) - 1);
-    const int num_kb = p.ntaps * p.cin_chunks;
     const uint32_t a_bytes = kBlockM * p.kchunk * 2, b_bytes = p.block_n * p.kchunk * 2;
 
     if (warp == 0 && lane == 0) {
@@ -132,14 +133,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
             for (int t = unit0; t < units; t += unit_step) {
-                const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
+                const int cls = t / cls_units, tt = t - cls * cls_units;
+                const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
+                const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * cs + crank;
                 const int m0 = m_blk * kBlockM;
                 // base pixel of the tile in the im2col "base pixel" space
                 const int img = m0 / (p.Po * p.Qo);
                 const int rem = m0 - img * (p.Po * p.Qo);
                 const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
                 const int bw = qi * p.tstride + p.lower_w, bh = pi * p.tstride + p.lower_h;
-                int tap = 0, cc = 0;
+                int tap = ncls > 1 ? p.cls_tap0[cls] : 0, cc = 0;
                 for (int g0 = 0; g0 < num_kb; g0 += kps) {
                     const int cnt = min(kps, num_kb - g0);         // k-blocks of this slot
                     PPROBE_T0;
@@ -184,6 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             PROBE_ACC(0);
             const uint32_t d_tmem = tmem_base + acc * p.block_n;
+            const int num_kb = (ncls > 1 ? p.cls_ntap[t / cls_units] : p.ntaps) * p.cin_chunks;
             for (int g0 = 0; g0 < num_kb; g0 += kps) {
                 const int cnt = min(kps, num_kb - g0);
                 PROBE_T0;
@@ -228,7 +232,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int slab_i = 0;                               // rotating output slab of this warp
         for (int t = unit0; t < units; t += unit_step, ++seq) {
             if ((seq & 1) != group) continue;
-            const int n_blk = t % p.tiles_n, m_blk = (t / p.tiles_n) * cs + crank;
+            const int cls = t / cls_units, tt = t - cls * cls_units;
+            const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * cs + crank;
             const int m = m_blk * kBlockM + quarter * 32 + lane;          // this thread's GEMM row
             const bool row_ok = m < p.M;
             // output row address (dense, or a strided parity class of a larger image)
@@ -237,7 +242,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int img = m / (p.Po * p.Qo);
                 const int rem = m - img * (p.Po * p.Qo);
                 const int pi = rem / p.Qo, qi = rem - pi * p.Qo;
-                orow = ((int64_t)img * p.OH + (pi * p.ostep + p.oh0)) * p.OW + (qi * p.ostep + p.ow0);
+                const int oh0 = ncls > 1 ? p.cls_oh0[cls] : p.oh0, ow0 = ncls > 1 ? p.cls_ow0[cls] : p.ow0;
+                orow = ((int64_t)img * p.OH + (pi * p.ostep + oh0)) * p.OW + (qi * p.ostep + ow0);
             }
             mbar_wait(&ctl->tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -281,7 +287,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmC, slab, n_blk * p.block_n + c * 32 - sub, m_blk * kBlockM + quarter * 32);
+                            if (p.flags & CONV_F_ACCUM) tma_reduce_add_2d(&tmC, slab, n_blk * p.block_n + c * 32 - sub, m_blk * kBlockM + quarter * 32);
+                            else tma_store_2d(&tmC, slab, n_blk * p.block_n + c * 32 - sub, m_blk * kBlockM + quarter * 32);
                             tma_store_commit();
                         }
                     }
@@ -455,7 +462,7 @@ int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtenso
         attr_set = true;
     }
     const int cs = p.cluster;
-    const int units = ((p.tiles_m + cs - 1) / cs) * p.tiles_n;
+    const int units = ((p.tiles_m + cs - 1) / cs) * p.tiles_n * (p.ncls > 1 ? p.ncls : 1);
     const int grid = std::min(units, sm_count() / cs) * cs;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

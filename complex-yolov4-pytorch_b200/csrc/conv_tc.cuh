@@ -49,6 +49,11 @@ struct ConvKParams {
     int omap, OH, OW, ostep, oh0, ow0;   // strided output-row mapping (stride-2 dgrad parity classes)
     const float *bias; float *ch_sum, *ch_sqsum;
     uint32_t flags;
+    // Several tap classes in ONE launch (stride-2 dgrad: the four output-parity classes, each with its own taps and output
+    // offsets, all over the same Po x Qo base-pixel grid).  Work unit t -> class t / cls_units.  ncls <= 1: one class made of
+    // taps [0, ntaps) and (oh0, ow0) above.
+    int ncls, cls_units;
+    uint8_t cls_tap0[4], cls_ntap[4], cls_oh0[4], cls_ow0[4];
     // fused epilogue
     int epi_mode, epi_act;
     const float *epi_scale, *epi_shift;  // per output channel

@@ -119,6 +119,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *s
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// Same box, but the tile is ADDED to global memory by the TMA / L2 (element type from the tensor map: fp16 add).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, const void *src, int c0, int c1)
+{
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // wait until at most `pending` (0, 1 or 3) of this thread's bulk store groups are still reading shared memory
