@@ -152,6 +152,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                 if (elect_one()) {
                     // descriptors as (lo, hi) halves: hi is a loop constant, lo advances by 16 pixel rows per MMA
                     const uint32_t a_lo0 = smem_desc_lo(a_base + stage * kWAStage, kPixBlk * 128);
+                    if (p.b_sw64 && ntap > 1) {
+                        // 32-channel X (64B swizzle): the taps' [128 px x 32 ch] slabs are consecutive 32-column blocks of ONE
+                        // MN-major B operand (LBO = slab size), so a single N = 32 * ntap MMA per K step replaces ntap MMAs of
+                        // N = 32 -- those are bound by the MMA dispatch rate (an N = 32 instruction costs as much issue time
+                        // as an N = 64 one), not by bytes.  The accumulator columns are the same: tap t at column 32 t.
+                        const uint32_t idesc_w = make_idesc_f16(128, 32 * ntap, 0, 1, 1);
+                        const uint32_t b_lo0 = smem_desc_lo(b_base + stage * kWBStage, b_tap_bytes);
+                        if (CY4_WDBG != 1) {
+#pragma unroll
+                            for (int k = 0; k < kPixBlk / 16; ++k)
+                                umma_f16_lohi(tmem_base, a_lo0 + k * (16 * 128 / 16), a_hi, b_lo0 + k * b_kstep, b_hi, idesc_w, (kb | k) != 0);
+                        }
+                    } else
                     for (int t = 0; t < ntap; ++t) {
                         const uint32_t b_addr = b_base + stage * kWBStage + t * b_tap_bytes;
                         const uint32_t b_lo0 = p.b_sw64 ? smem_desc_lo(b_addr, 0) : smem_desc_lo(b_addr, kPixBlk * 128);
