@@ -26,6 +26,7 @@ int g_kps_max = 4;         // k-blocks per pipeline slot (upper bound; 1 disable
 int g_conv_pair = 1;        // CTA-pair (cta_group::2) conv kernel for the eligible launches (conv_pair.cu); 0: always the 1-CTA kernel
 int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUSTER")) : 1;
 int g_wgrad_pair = 1;       // CTA-pair weight-gradient kernel for the eligible launches (conv_wgrad.cu conv_wgrad_pair_kernel)
+int g_wgrad_wide32 = 1;     // weight gradient of 32-channel inputs: the taps of a CTA as ONE N = 32*taps MMA operand
 int g_accum_tma = 1;        // accumulate-mode outputs through TMA reduce-add stores (0: per-thread read-modify-write)
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
@@ -354,6 +355,7 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "wgrad_cluster")) { CY4_CHECK_ARG(value == 1 || value == 2, "wgrad_cluster must be 1 or 2"); g_wgrad_cluster = value; return 0; }
     if (!strcmp(name, "tma_store")) { g_disable_tma_out = value ? 0 : 1; return 0; }
     if (!strcmp(name, "kblocks_per_slot")) { g_kps_max = value < 1 ? 1 : (value > 8 ? 8 : value); return 0; }
+    if (!strcmp(name, "wgrad_wide32")) { g_wgrad_wide32 = value ? 1 : 0; return 0; }
     if (!strcmp(name, "accum_tma")) { g_accum_tma = value ? 1 : 0; return 0; }
     if (!strcmp(name, "wgrad_pair")) { g_wgrad_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv1x1_matrix")) { g_conv1x1_matrix = value ? 1 : 0; return 0; }

@@ -23,6 +23,7 @@ namespace cy4 {
 using namespace sm100;
 extern int g_wgrad_cluster;      // conv_api.cu (cy4_set_option)
 extern int g_debug;              // 1: skip the MMAs, 2: skip the TMA loads (bottleneck experiments only)
+extern int g_wgrad_wide32;       // conv_api.cu ("wgrad_wide32"): one N = 32*taps MMA per K step for 32-channel X instead of one per tap
 extern int g_wgrad_pair;         // conv_api.cu (cy4_set_option "wgrad_pair"): CTA-pair kernel for the eligible launches
 
 // The TMA unit sustains roughly one bulk-tensor instruction per ~350 cycles per SM regardless of the
@@ -42,6 +43,7 @@ struct WgradParams {
     int tpc, tap_groups;         // taps handled by one CTA (accumulators tpc * block_n TMEM columns <= 256)
     int cluster;                 // CTAs per cluster (consecutive m tiles) sharing every X slab through TMA multicast
     int pair;                    // 1: conv_wgrad_pair_kernel (cta_group::2)
+    int wide32;                  // 1: 32-channel X taps as one wide-N B operand
     int debug;
     int b_boxes;                 // block_n / 64 (or 1 when the 64B-swizzle N=32 path is used)
     int b_sw64;                  // 1: X has 32 channels, single [64 px x 32 ch] box, 64B swizzle
@@ -152,7 +154,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                 if (elect_one()) {
                     // descriptors as (lo, hi) halves: hi is a loop constant, lo advances by 16 pixel rows per MMA
                     const uint32_t a_lo0 = smem_desc_lo(a_base + stage * kWAStage, kPixBlk * 128);
-                    if (p.b_sw64 && ntap > 1) {
+                    if (p.b_sw64 && ntap > 1 && p.wide32) {
                         // 32-channel X (64B swizzle): the taps' [128 px x 32 ch] slabs are consecutive 32-column blocks of ONE
                         // MN-major B operand (LBO = slab size), so a single N = 32 * ntap MMA per K step replaces ntap MMAs of
                         // N = 32 -- those are bound by the MMA dispatch rate (an N = 32 instruction costs as much issue time
@@ -369,6 +371,7 @@ static void wgrad_tiling(const cy4_conv_desc *d, WgradParams &p)
     p.tap_groups = (p.ntaps + p.tpc - 1) / p.tpc;
     // pairs of CTAs on consecutive m tiles share (multicast) the X slabs; not for the matrix (stem) mode
     p.debug = g_debug;
+    p.wide32 = g_wgrad_wide32;
     p.cluster = (g_wgrad_cluster >= 2 && !(d->flags & CY4_CONV_A_MATRIX) && p.m_tiles % 2 == 0) ? 2 : 1;
     // CTA pairs (conv_wgrad_pair_kernel): both m tiles of a pair full, an even number of 64-channel X boxes per tap
     p.pair = (g_wgrad_pair && !(d->flags & CY4_CONV_A_MATRIX) && !sw64 && d->Cout % 256 == 0 && p.block_n >= 128 && p.cluster == 1) ? 1 : 0;

@@ -64,7 +64,6 @@ __global__ void bn_finalize_kernel(const float *__restrict__ ch_sum, const float
 // vectors-per-row > 256 (C > 2048) is handled by an outer loop.  Templated on the activation so the
 // Mish / LeakyReLU math is branch-free.
 constexpr int kUnroll = 4;
-constexpr int kHalf = kUnroll / 2;                       // row groups per stage of the software-pipelined passes
 
 
 struct RowChunk { int64_t begin, end; };
@@ -132,23 +131,18 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
             for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
         }
         const RowChunk rc = block_rows(M, rpi);
-        // Software pipeline: two register stages of kHalf row groups; the loads of the next stage are in flight while the current
-        // one is evaluated (the Mish pass is MUFU / issue heavy: without this the memory pipe idles during the arithmetic).
-        const int64_t step = (int64_t)rpi * kHalf;
-        uint4 ya[kHalf], ra[kHalf], yb[kHalf], rb[kHalf];
-        auto load = [&](uint4 (&vy)[kHalf], uint4 (&vr)[kHalf], int64_t m) {
+        for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
+            uint4 vy[kUnroll], vr[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kHalf; ++u) {
+            for (int u = 0; u < kUnroll; ++u) {
                 const int64_t mm = m + u * rpi;
                 if (mm < rc.end) {
                     vy[u] = *(const uint4 *)(y + mm * ldy + c0);
                     if (RES) vr[u] = *(const uint4 *)(res + mm * ldr + c0);
                 }
             }
-        };
-        auto compute = [&](const uint4 (&vy)[kHalf], const uint4 (&vr)[kHalf], int64_t m) {
 #pragma unroll
-            for (int u = 0; u < kHalf; ++u) {
+            for (int u = 0; u < kUnroll; ++u) {
                 const int64_t mm = m + u * rpi;
                 if (mm < rc.end) {
                     float f[8], r[8];
@@ -162,20 +156,6 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
                     }
                     *(uint4 *)(out + mm * ldo + c0) = pack8(f);
                 }
-            }
-        };
-        int64_t m = rc.begin + rsub;
-        if (m < rc.end) {
-            load(ya, ra, m);
-            while (true) {
-                if (m + step < rc.end) load(yb, rb, m + step);
-                compute(ya, ra, m);
-                m += step;
-                if (m >= rc.end) break;
-                if (m + step < rc.end) load(ya, ra, m + step);
-                compute(yb, rb, m);
-                m += step;
-                if (m >= rc.end) break;
             }
         }
     }
@@ -205,18 +185,15 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, __half *__re
 #pragma unroll
             for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
             const RowChunk rc = block_rows(M, rpi);
-            const int64_t step = (int64_t)rpi * kHalf;                  // software pipeline, see bn_act_fwd_kernel
-            uint4 ya[kHalf], ga[kHalf], yb[kHalf], gb[kHalf];
-            auto load = [&](uint4 (&vy)[kHalf], uint4 (&vg)[kHalf], int64_t m) {
+            for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
+                uint4 vy[kUnroll], vg[kUnroll];
 #pragma unroll
-                for (int u = 0; u < kHalf; ++u) {
+                for (int u = 0; u < kUnroll; ++u) {
                     const int64_t mm = m + u * rpi;
                     if (mm < rc.end) { vy[u] = *(const uint4 *)(y + mm * ldy + c0); vg[u] = *(const uint4 *)(dA + mm * ldg + c0); }
                 }
-            };
-            auto compute = [&](const uint4 (&vy)[kHalf], const uint4 (&vg)[kHalf], int64_t m) {
 #pragma unroll
-                for (int u = 0; u < kHalf; ++u) {
+                for (int u = 0; u < kUnroll; ++u) {
                     const int64_t mm = m + u * rpi;
                     if (mm < rc.end) {
                         float fy[8], fg[8];
@@ -230,20 +207,6 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, __half *__re
                         }
                         if (ACT != ACT_LINEAR) *(uint4 *)(dA + mm * ldg + c0) = pack8(fg);   // dz replaces dA (fp16)
                     }
-                }
-            };
-            int64_t m = rc.begin + rsub;
-            if (m < rc.end) {
-                load(ya, ga, m);
-                while (true) {
-                    if (m + step < rc.end) load(yb, gb, m + step);
-                    compute(ya, ga, m);
-                    m += step;
-                    if (m >= rc.end) break;
-                    if (m + step < rc.end) load(ya, ga, m + step);
-                    compute(yb, gb, m);
-                    m += step;
-                    if (m >= rc.end) break;
                 }
             }
         }

@@ -151,6 +151,7 @@ typedef struct cy4_conv_desc {
  * slabs through TMA multicast; "tma_store" (0|1): swizzled-smem + TMA-store epilogue of the fp16 outputs;
  * "kblocks_per_slot" (1..8, default 4): upper bound on the k-blocks of a narrow layer packed into one pipeline slot;
  * "conv1x1_matrix" (0|1): 1 = 1x1 / stride-1 convs read their activation through a plain 2-D tiled TMA instead of im2col mode;
+ * "wgrad_wide32" (0|1, default 1): weight gradient of 32-channel inputs issues one N = 32*taps MMA per K step instead of one per tap;
  * "accum_tma" (0|1, default 1): CY4_CONV_ACCUM outputs through TMA reduce-add stores instead of per-thread read-modify-write;
  * "wgrad_pair" (0|1, default 1): CTA-pair weight-gradient kernel for layers with Cout % 256 == 0 and a 128/256-channel X tile;
  * "conv_pair" (0|1, default 1): CTA-pair (tcgen05 cta_group::2, 256-row tiles) kernel for the eligible conv launches;
