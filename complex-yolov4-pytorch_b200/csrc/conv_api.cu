@@ -40,7 +40,7 @@ struct GenericConv {
     int N;                                             // real output channels
     void *y; int64_t ldy; uint32_t flags;
     int omap, OH, OW, ostep, oh0, ow0;
-    const float *bias; float *ch_sum, *ch_sqsum;
+    const float *bias; float *ch_sum, *ch_sqsum; const float *stat_shift;
     int a_matrix;
     int epi_mode, epi_act; const float *epi_scale, *epi_shift; const void *side; int64_t ld_side;   // fused epilogue (conv_tc.cuh)
     int ncls; uint8_t cls_tap0[4], cls_ntap[4], cls_oh0[4], cls_ow0[4];                              // tap classes merged into one launch
@@ -66,7 +66,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     for (int t = 0; t < g.ntaps; ++t) { p.tap_ow[t] = g.ow[t]; p.tap_oh[t] = g.oh[t]; p.tap_kofs[t] = g.kofs[t]; }
     p.y = g.y; p.ldy = g.ldy; p.flags = g.flags;
     p.omap = g.omap; p.OH = g.OH; p.OW = g.OW; p.ostep = g.ostep; p.oh0 = g.oh0; p.ow0 = g.ow0;
-    p.bias = g.bias; p.ch_sum = g.ch_sum; p.ch_sqsum = g.ch_sqsum;
+    p.bias = g.bias; p.ch_sum = g.ch_sum; p.ch_sqsum = g.ch_sqsum; p.stat_shift = g.stat_shift;
     p.epi_mode = g.epi_mode; p.epi_act = g.epi_act; p.epi_scale = g.epi_scale; p.epi_shift = g.epi_shift;
     p.side = g.side; p.ld_side = g.ld_side;
     p.ncls = g.ncls;
@@ -365,7 +365,7 @@ int cy4_set_option(const char *name, int value)
     return -1;
 }
 
-struct EpiArgs { int mode, act; const float *scale, *shift; const void *side; int64_t ld_side; };
+struct EpiArgs { int mode, act; const float *scale, *shift; const void *side; int64_t ld_side; const float *stat_shift; };
 
 static int conv_fwd_impl(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias, float *ch_sum,
                          float *ch_sqsum, const EpiArgs *epi, void *stream)
@@ -396,8 +396,18 @@ static int conv_fwd_impl(const cy4_conv_desc *d, const void *x, const void *w_fp
     g.a_matrix = (d->flags & CY4_CONV_A_MATRIX) ? 1 : 0;
     if (g.a_matrix) CY4_CHECK_ARG(k == 1 && d->stride == 1 && d->pad == 0, "cy4_conv_fwd: matrix mode needs a 1x1/s1/p0 conv");
     if (g_conv1x1_matrix && k == 1 && d->stride == 1 && d->pad == 0) g.a_matrix = 1;
-    if (epi) { g.epi_mode = epi->mode; g.epi_act = epi->act; g.epi_scale = epi->scale; g.epi_shift = epi->shift; g.side = epi->side; g.ld_side = epi->ld_side; }
+    if (epi) { g.epi_mode = epi->mode; g.epi_act = epi->act; g.epi_scale = epi->scale; g.epi_shift = epi->shift; g.side = epi->side; g.ld_side = epi->ld_side;
+               g.stat_shift = epi->stat_shift; }
     return run_generic(g, (cudaStream_t)stream);
+}
+
+int cy4_conv_fwd_stats(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, float *ch_sum, float *ch_sqsum,
+                       const float *stat_shift, void *stream)
+{
+    CY4_CHECK_ARG(d && (d->flags & CY4_CONV_STATS) && ch_sum && ch_sqsum, "cy4_conv_fwd_stats: needs CY4_CONV_STATS and the two sum arrays");
+    CY4_CHECK_ARG(d->Cout % 32 == 0, "cy4_conv_fwd_stats: Cout must be a multiple of 32");
+    const EpiArgs e = {EPI_NONE, 0, nullptr, nullptr, nullptr, 0, stat_shift};
+    return conv_fwd_impl(d, x, w_fprop, y, nullptr, ch_sum, ch_sqsum, &e, stream);
 }
 
 int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias, float *ch_sum,
@@ -413,7 +423,7 @@ int cy4_conv_fwd_fused(const cy4_conv_desc *d, const void *x, const void *w_fpro
     CY4_CHECK_ARG(!(d->flags & (CY4_CONV_OUT_F32 | CY4_CONV_STATS | CY4_CONV_ACCUM)), "cy4_conv_fwd_fused: fp16 output without statistics / accumulation only");
     CY4_CHECK_ARG(d->Cout % 32 == 0, "cy4_conv_fwd_fused: Cout must be a multiple of 32");
     CY4_CHECK_ARG(!residual || (ldr % 8 == 0 && ldr >= d->Cout), "cy4_conv_fwd_fused: residual ld");
-    const EpiArgs e = {EPI_FWD_ACT, act, nullptr, shift, residual, ldr};
+    const EpiArgs e = {EPI_FWD_ACT, act, nullptr, shift, residual, ldr, nullptr};
     return conv_fwd_impl(d, x, w_fprop, y, nullptr, nullptr, nullptr, &e, stream);
 }
 
@@ -430,7 +440,7 @@ int cy4_conv_dgrad_fused(const cy4_conv_desc *d, const void *dy, const void *w_d
 {
     CY4_CHECK_ARG(d && y_producer && scale && shift && sum_dz && sum_dzy && act >= 0 && act <= 2, "cy4_conv_dgrad_fused: bad argument");
     CY4_CHECK_ARG(ldyp % 8 == 0 && ldyp >= d->Cin, "cy4_conv_dgrad_fused: producer ld");
-    const EpiArgs e = {EPI_BWD_DZ, act, scale, shift, y_producer, ldyp};
+    const EpiArgs e = {EPI_BWD_DZ, act, scale, shift, y_producer, ldyp, nullptr};
     return conv_dgrad_impl(d, dy, w_dgrad, dx, &e, sum_dz, sum_dzy, stream);
 }
 

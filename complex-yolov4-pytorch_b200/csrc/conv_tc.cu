@@ -339,6 +339,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float s1[32], s2[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { s1[i] = f[i]; s2[i] = f[i] * (p.epi_mode == EPI_BWD_DZ ? g[i] : f[i]); }
+                    if (p.stat_shift) {
+                        // shifted sums: sum (y - c), sum (y - c)^2 with c ~ the channel mean (last step's): the batch variance
+                        // s2/n - (s1/n)^2 then has no cancellation however large |mean| / sigma is.  Rows beyond M are exact
+                        // zeros of the GEMM, not samples: they must not contribute -c.
+                        const float4 *c4 = (const float4 *)(p.stat_shift + n0);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 cv = __ldg(c4 + (i >> 2));
+                            const float d0 = row_ok ? f[i] - cv.x : 0.f, d1 = row_ok ? f[i + 1] - cv.y : 0.f;
+                            const float d2 = row_ok ? f[i + 2] - cv.z : 0.f, d3 = row_ok ? f[i + 3] - cv.w : 0.f;
+                            s1[i] = d0; s1[i + 1] = d1; s1[i + 2] = d2; s1[i + 3] = d3;
+                            s2[i] = d0 * d0; s2[i + 1] = d1 * d1; s2[i + 2] = d2 * d2; s2[i + 3] = d3 * d3;
+                        }
+                    }
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
                         const bool hi = (lane & off) != 0;

@@ -48,6 +48,7 @@ struct ConvKParams {
     void *y; int64_t ldy;
     int omap, OH, OW, ostep, oh0, ow0;   // strided output-row mapping (stride-2 dgrad parity classes)
     const float *bias; float *ch_sum, *ch_sqsum;
+    const float *stat_shift;     // CONV_F_STATS: NULL, or per-channel c[n]: the sums are of (y - c) and (y - c)^2 (rows >= M excluded)
     uint32_t flags;
     // Several tap classes in ONE launch (stride-2 dgrad: the four output-parity classes, each with its own taps and output
     // offsets, all over the same Po x Qo base-pixel grid).  Work unit t -> class t / cls_units.  ncls <= 1: one class made of

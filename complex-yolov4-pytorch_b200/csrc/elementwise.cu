@@ -84,6 +84,8 @@ struct BnFin {
     const float *ch_sum, *ch_sqsum, *gamma, *beta;
     float *running_mean, *running_var; long long *num_batches;
     float *scale_out, *shift_out, *mean_out, *rstd_out;
+    const float *stat_shift;      // NULL, or c[ch]: ch_sum / ch_sqsum are sums of (y - c), (y - c)^2 (cy4_conv_fwd_stats)
+    float *shift_next;            // NULL, or where the batch mean is published as the NEXT step's c (never the array read above)
     float count, momentum, eps;
     double inv_count;
 };
@@ -112,9 +114,10 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
                 const int c = c0 + k;
                 // same arithmetic as bn_finalize_kernel (double mean / variance), with the divisions by the count turned into
                 // one multiplication by its double reciprocal: every thread of the grid executes this prologue
-                const double m = (double)fin.ch_sum[c] * fin.inv_count;
-                double v = (double)fin.ch_sqsum[c] * fin.inv_count - m * m;
+                const double ms = (double)fin.ch_sum[c] * fin.inv_count;              // mean of (y - c)
+                double v = (double)fin.ch_sqsum[c] * fin.inv_count - ms * ms;         // variance is shift invariant
                 if (v < 0.0) v = 0.0;
+                const double m = ms + (fin.stat_shift ? (double)fin.stat_shift[c] : 0.0);
                 const float mean = (float)m, var = (float)v;
                 const float rstd = rsqrtf(var + fin.eps);
                 sc[k] = fin.gamma[c] * rstd;
@@ -124,6 +127,7 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
                     fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mean;
                     fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * unbiased;
                     fin.scale_out[c] = sc[k]; fin.shift_out[c] = sh[k]; fin.mean_out[c] = mean; fin.rstd_out[c] = rstd;
+                    if (fin.shift_next) fin.shift_next[c] = mean;
                 }
             }
         } else {
@@ -559,9 +563,10 @@ int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *
 int cy4_bn_train_act_fwd(const void *y, int64_t ldy, const float *ch_sum, const float *ch_sqsum, float count, const float *gamma,
                          const float *beta, float *running_mean, float *running_var, int64_t *num_batches_tracked, float momentum,
                          float eps, float *scale, float *shift, float *mean, float *rstd, int act, const void *residual, int64_t ldr,
-                         void *out, int64_t ldo, int64_t M, int C, void *stream)
+                         void *out, int64_t ldo, int64_t M, int C, const float *stat_shift, float *shift_next, void *stream)
 {
     EW_CHECK_C(C, "cy4_bn_train_act_fwd");
+    CY4_CHECK_ARG(!shift_next || shift_next != stat_shift, "cy4_bn_train_act_fwd: shift_next must not alias stat_shift (every block reads it)");
     CY4_CHECK_ARG(y && ch_sum && ch_sqsum && gamma && beta && running_mean && running_var && scale && shift && mean && rstd && out &&
                   count > 0 && M > 0 && (ldy % 8) == 0 && (ldo % 8) == 0 && (ldr % 8) == 0, "cy4_bn_train_act_fwd: bad argument");
     BnFin f;
@@ -569,6 +574,7 @@ int cy4_bn_train_act_fwd(const void *y, int64_t ldy, const float *ch_sum, const 
     f.running_mean = running_mean; f.running_var = running_var; f.num_batches = (long long *)num_batches_tracked;
     f.scale_out = scale; f.shift_out = shift; f.mean_out = mean; f.rstd_out = rstd;
     f.count = count; f.momentum = momentum; f.eps = eps; f.inv_count = 1.0 / (double)count;
+    f.stat_shift = stat_shift; f.shift_next = shift_next;
     return bn_act_fwd_launch(y, ldy, nullptr, nullptr, act, residual, ldr, out, ldo, M, C, &f, stream);
 }
 

@@ -46,7 +46,8 @@ SIGS = {
     "cy4_bn_finalize": (c_i, [c_f, c_f, ctypes.c_float, c_f, c_f, c_f, c_f, c_f, ctypes.c_float, ctypes.c_float, c_i, c_i,
                                 c_f, c_f, c_f, c_f, c_vp]),
     "cy4_bn_train_act_fwd": (c_i, [c_f, c_i64, c_f, c_f, ctypes.c_float, c_f, c_f, c_f, c_f, c_f, ctypes.c_float, ctypes.c_float,
-                                     c_f, c_f, c_f, c_f, c_i, c_f, c_i64, c_f, c_i64, c_i64, c_i, c_vp]),
+                                     c_f, c_f, c_f, c_f, c_i, c_f, c_i64, c_f, c_i64, c_i64, c_i, c_f, c_f, c_vp]),
+    "cy4_conv_fwd_stats": (c_i, [PD, c_f, c_f, c_f, c_f, c_f, c_f, c_vp]),
     "cy4_bn_act_fwd": (c_i, [c_f, c_i64, c_f, c_f, c_i, c_f, c_i64, c_f, c_i64, c_i64, c_i, c_vp]),
     "cy4_bn_act_bwd_reduce": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_f, c_f, c_f, c_i, c_i64, c_i, c_f, c_f, c_vp]),
     "cy4_bn_bwd_fixup": (c_i, [c_f, c_f, c_f, c_f, c_i, c_vp]),

@@ -175,6 +175,7 @@ class Darknet(nn.Module):
         self.grad_scale_target = 256.0  # the fp16 gradient tensors are scaled so that max |d loss / d head| ~ this
         self.sync_outputs = False       # True: the CPU detections are complete when forward returns (training)
         self.use_cuda_graph = False     # True: after 2 eager steps the fwd / bwd launch sequences are replayed as CUDA graphs
+        self.bn_shifted_stats = True    # training: BN statistics summed about the previous step's batch mean (no E[y^2]-E[y]^2 cancellation)
         self.engine_allreduce = False   # True (set by models.model_utils.make_data_parallel): the engine averages gradients over the ranks
                                         # itself, overlapped with backward; DDP then carries a no-op communication hook
         self.allreduce_groups = 6       # number of gradient groups of that exchange

@@ -26,7 +26,7 @@ from . import convops as co
 from .yolo import LazyMetrics, make_desc, check_status
 
 ACT = {"linear": 0, "leaky": 1, "mish": 2}
-_PROFILED = ("cy4_conv_fwd", "cy4_conv_dgrad", "cy4_conv_dgrad_fused", "cy4_conv_wgrad")
+_PROFILED = ("cy4_conv_fwd", "cy4_conv_fwd_stats", "cy4_conv_dgrad", "cy4_conv_dgrad_fused", "cy4_conv_wgrad")
 
 
 def rup(x, m):
@@ -507,6 +507,11 @@ class Plan:
         self.stats = f32(2, tc)            # sum, sum of squares (zeroed every forward)
         self.bnq = f32(4, tc)              # scale, shift, mean, rstd
         self.dbn = f32(2, tc)              # d beta, d gamma (under the loss scale), zeroed every backward
+        # BatchNorm statistics are summed about a per-channel shift c = the previous step's batch mean (cy4_conv_fwd_stats): no
+        # cancellation in E[y^2] - E[y]^2 however large |mean| / sigma grows during training.  The apply pass publishes the new
+        # mean into shift_next; it becomes shift_cur at the start of the next forward (never while a kernel reads it).
+        self.shift_cur, self.shift_next = f32(tc), f32(tc)
+        self.shifted_stats = bool(getattr(model, "bn_shifted_stats", True)) and not self.infer
         # weight packs / gradient accumulators ([Cout_pad][taps][Cin] fp32, one flat buffer, one memset)
         wtot, atot = 0, 0
         for rec in self.convs:
@@ -679,6 +684,8 @@ class Plan:
         self._x = x
         self._pack_weights(st)
         self.stats.zero_()
+        if training and self.shifted_stats:
+            self.shift_cur.copy_(self.shift_next)
         total = None
         if targets is not None:
             tg = targets.detach().to(self.device, torch.float32).contiguous()
@@ -749,13 +756,19 @@ class Plan:
             d.ldy = Y.ld
             d.flags = amat | (co.CONV_STATS if training else 0)
             s1 = self.stats[0, c0:].data_ptr(); s2 = self.stats[1, c0:].data_ptr()
-            self._call(L.cy4_conv_fwd, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), Y.buf.data_ptr(), None, s1, s2, st)
+            shifted = training and self.shifted_stats
+            if shifted:
+                self._call(L.cy4_conv_fwd_stats, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), Y.buf.data_ptr(), s1, s2,
+                           self.shift_cur[c0:].data_ptr(), st)
+            else:
+                self._call(L.cy4_conv_fwd, ctypes.byref(d), src_ptr, rec["wf"].data_ptr(), Y.buf.data_ptr(), None, s1, s2, st)
             q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
             if training:      # batch statistics -> scale / shift inside the apply pass (one launch)
                 self._call(L.cy4_bn_train_act_fwd, Y.buf.data_ptr(), Y.ld, s1, s2, float(Y.M), bn.weight.data_ptr(), bn.bias.data_ptr(),
                            bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), float(bn.momentum),
                            float(bn.eps), q[0], q[1], q[2], q[3], rec["act"], res.ptr if res is not None else None,
-                           res.ld if res is not None else 0, A.ptr, A.ld, Y.M, Cout, st)
+                           res.ld if res is not None else 0, A.ptr, A.ld, Y.M, Cout,
+                           self.shift_cur[c0:].data_ptr() if shifted else None, self.shift_next[c0:].data_ptr() if shifted else None, st)
             else:
                 self._call(L.cy4_bn_finalize, s1, s2, float(Y.M), bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                            bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), float(bn.momentum), float(bn.eps),

@@ -160,6 +160,12 @@ CY4_API int cy4_set_option(const char *name, int value);
 /* y = conv(x, w) */
 CY4_API int cy4_conv_fwd(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, const float *bias,
                          float *ch_sum, float *ch_sqsum, void *stream);
+/* cy4_conv_fwd with CY4_CONV_STATS, the statistics taken about a per-channel shift c[Cout] (NULL = 0): ch_sum += sum (y - c),
+ * ch_sqsum += sum (y - c)^2.  With c close to the channel mean (the engine passes last step's batch mean) the batch variance
+ * ch_sqsum/n - (ch_sum/n)^2 is free of the cancellation that E[y^2] - E[y]^2 suffers once |mean| >> sigma; the mean is
+ * c + ch_sum/n (cy4_bn_train_act_fwd takes the same c). */
+CY4_API int cy4_conv_fwd_stats(const cy4_conv_desc *d, const void *x, const void *w_fprop, void *y, float *ch_sum, float *ch_sqsum,
+                               const float *stat_shift, void *stream);
 /* Eval-mode inference: y = act(conv(x, w_folded) + shift[c]) (+ residual), fp16 NHWC.  BatchNorm
  * (running statistics) is folded into the packed weights (cy4_pack_item.fold_scale) and `shift` = beta - mean*scale;
  * Mish / LeakyReLU run in the conv epilogue on the fp32 accumulators; `residual` (NULL or fp16 [B*Ho*Wo, ldr]) is the
@@ -234,7 +240,10 @@ CY4_API int cy4_bn_finalize(const float *ch_sum, const float *ch_sqsum, float co
 CY4_API int cy4_bn_train_act_fwd(const void *y, int64_t ldy, const float *ch_sum, const float *ch_sqsum, float count, const float *gamma,
                                  const float *beta, float *running_mean, float *running_var, int64_t *num_batches_tracked,
                                  float momentum, float eps, float *scale, float *shift, float *mean, float *rstd, int act,
-                                 const void *residual, int64_t ldr, void *out, int64_t ldo, int64_t M, int C, void *stream);
+                                 const void *residual, int64_t ldr, void *out, int64_t ldo, int64_t M, int C,
+                                 const float *stat_shift /* the c of cy4_conv_fwd_stats, or NULL */,
+                                 float *shift_next /* NULL, or [C]: receives the batch mean (next step's c); must not alias stat_shift */,
+                                 void *stream);
 /* out = act(y*scale + shift) (+ residual) */
 CY4_API int cy4_bn_act_fwd(const void *y, int64_t ldy, const float *scale, const float *shift, int act, const void *residual,
                            int64_t ldr, void *out, int64_t ldo, int64_t M, int C, void *stream);

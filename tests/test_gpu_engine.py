@@ -339,8 +339,20 @@ def test_elementwise_kernels_vs_torch():
         q3 = torch.zeros(4, C, device="cuda"); out3 = torch.empty_like(y16)
         _lib.check(L.cy4_bn_train_act_fwd(y16.data_ptr(), C, s1.data_ptr(), s2.data_ptr(), float(M), gamma.data_ptr(), beta.data_ptr(),
                                           rm3.data_ptr(), rv3.data_ptr(), nbt3.data_ptr(), 0.1, 1e-5, q3[0].data_ptr(), q3[1].data_ptr(),
-                                          q3[2].data_ptr(), q3[3].data_ptr(), act_id, None, 0, out3.data_ptr(), C, M, C, st))
+                                          q3[2].data_ptr(), q3[3].data_ptr(), act_id, None, 0, out3.data_ptr(), C, M, C, None, None, st))
         assert torch.equal(out3, out) and torch.equal(q3, q) and torch.equal(rm3, rm) and torch.equal(rv3, rv) and int(nbt3) == 1
+        # statistics taken about a shift c (cy4_conv_fwd_stats): same mean / variance, published as the next shift
+        cshift = (yf.detach().mean((0, 1, 2)) + 0.01).contiguous()
+        d = yf.detach() - cshift
+        s1c = d.sum((0, 1, 2)).contiguous(); s2c = (d * d).sum((0, 1, 2)).contiguous()
+        rm4 = torch.zeros(C, device="cuda"); rv4 = torch.ones(C, device="cuda"); nbt4 = torch.zeros(1, device="cuda", dtype=torch.int64)
+        q4 = torch.zeros(4, C, device="cuda"); out4 = torch.empty_like(y16); nxt = torch.zeros(C, device="cuda")
+        _lib.check(L.cy4_bn_train_act_fwd(y16.data_ptr(), C, s1c.data_ptr(), s2c.data_ptr(), float(M), gamma.data_ptr(), beta.data_ptr(),
+                                          rm4.data_ptr(), rv4.data_ptr(), nbt4.data_ptr(), 0.1, 1e-5, q4[0].data_ptr(), q4[1].data_ptr(),
+                                          q4[2].data_ptr(), q4[3].data_ptr(), act_id, None, 0, out4.data_ptr(), C, M, C, cshift.data_ptr(),
+                                          nxt.data_ptr(), st))
+        assert torch.allclose(q4, q, rtol=2e-5, atol=2e-6) and torch.allclose(nxt, q[2], rtol=1e-5, atol=1e-6)
+        assert (out4.float() - out.float()).abs().max().item() <= 4e-3
         rm2 = torch.zeros(C, device="cuda"); rv2 = torch.ones(C, device="cuda")
         z = F.batch_norm(yf.permute(0, 3, 1, 2), rm2, rv2, gamma, beta, True, 0.1, 1e-5)
         ref = act(z).permute(0, 2, 3, 1)
