@@ -486,10 +486,29 @@ static int conv_dgrad_impl(const cy4_conv_desc *d, const void *dy, const void *w
     g.lower_w = g.lower_h = 0; g.upper_w = g.upper_h = 0; g.tstride = 1;
     g.Po = d->Hi / 2; g.Qo = d->Wi / 2;
     g.omap = 1; g.OH = d->Hi; g.OW = d->Wi; g.ostep = 2;
-    // All four parity classes in ONE launch (work unit -> class): a single grid instead of four part-filled ones.
     static const int cls_n[2] = {1, 2};
     static const int cls_r[2][2] = {{1, 0}, {0, 2}};
     static const int cls_o[2][2] = {{0, 0}, {1, 0}};
+    if (pick_block_n(g.w_rows_pad) <= 32) {
+        // Narrow input (Cin = 32): these tiles are bound by the issue threads and pack several k-blocks per pipeline slot; the
+        // packing factor is per launch, and the 1-tap class would force 1 -- one launch per parity class (measured faster here).
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                g.oh0 = ph; g.ow0 = pw;
+                g.ntaps = 0;
+                for (int a = 0; a < cls_n[ph]; ++a)
+                    for (int b = 0; b < cls_n[pw]; ++b) {
+                        const int t = g.ntaps++;
+                        g.oh[t] = (uint8_t)cls_o[ph][a]; g.ow[t] = (uint8_t)cls_o[pw][b];
+                        g.kofs[t] = (cls_r[ph][a] * 3 + cls_r[pw][b]) * d->Cout;
+                    }
+                const int rc = run_generic(g, (cudaStream_t)stream);
+                if (rc) return rc;
+            }
+        return 0;
+    }
+    // All four parity classes in ONE launch (work unit -> class): a single grid instead of four part-filled ones
+    // (-20...45 % on the wide layers, profiles/r2_conv_shape_bench.md).
     g.ntaps = 0; g.ncls = 0;
     for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
