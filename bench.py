@@ -109,6 +109,11 @@ def run_ours(args):
     torch.manual_seed(0)
     net = Darknet(netdefs.cfg_path(args.cfg), use_giou_loss=True).to(dev).train()
     net.use_cuda_graph = bool(args.cuda_graph)
+    for o in args.model_opt:
+        name, val = o.split("=")
+        if not hasattr(net, name):
+            raise SystemExit("--model-opt: the model has no attribute %r" % name)
+        setattr(net, name, int(val))
     model = net
     if world > 1 or args.force_ddp:
         # unchanged PyTorch DDP (parameter broadcast, bucket views); the gradient all-reduce itself is issued by the engine in
@@ -272,7 +277,11 @@ def run_ours(args):
                 top_shapes = [{"error": repr(e)[:200]}]
             conv_ms = sum(v[0] for v in agg.values()) / 2
             tc = {n: {"ms_per_step": v[0] / 2, "tflops": v[1] / (v[0] * 1e9) if v[0] else 0.0, "launches_per_step": v[2] // 2} for n, v in agg.items()}
-            fwd = agg.get("cy4_conv_fwd", [1e-9, 0, 1])
+            # fprop family: cy4_conv_fwd (heads, eval) + cy4_conv_fwd_stats (training-mode BN layers, shifted statistics)
+            fwd = [1e-9, 0.0, 0]
+            for n_ in ("cy4_conv_fwd", "cy4_conv_fwd_stats"):
+                if n_ in agg:
+                    fwd = [fwd[0] + agg[n_][0], fwd[1] + agg[n_][1], fwd[2] + agg[n_][2]]
             achieved = fwd[1] / (fwd[0] * 1e9)
             # dram read+write bytes per fprop launch: from this round's `ncu --set full` capture of the shipped kernel over the
             # same workload (profiles/r2_conv_fprop_traffic.json, written by tools/ncu_summarise.py); null when no capture of
@@ -369,7 +378,8 @@ def run_ours(args):
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "no flush needed: per-step working set (>20 GB) exceeds the 126 MB L2",
                        "optimizer": "torch.optim.Adam(%s), reference parameter groups (train_utils.py:21-50)" % ("foreach" if args.adam_foreach else "fused=True"),
-                       "cuda_graph": graph_note, **({"options": args.opt} if args.opt else {})},
+                       "cuda_graph": graph_note, **({"options": args.opt} if args.opt else {}),
+                       **({"model_options": args.model_opt} if args.model_opt else {})},
             "e2e": {"value": round(world * B * args.steps / float(e2e_s.item()), 2), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "last_loss": lval},
             "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps,
@@ -576,6 +586,8 @@ def main():
                     help="1 (default): after two eager steps the fwd / bwd launch sequences (~850 kernels) are replayed as CUDA graphs; 0: eager launches")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT",
                     help="cy4_set_option(NAME, INT) before the run (kernel experiments, e.g. conv_cluster=2); recorded in config")
+    ap.add_argument("--model-opt", dest="model_opt", action="append", default=[], metavar="NAME=INT",
+                    help="engine experiments: setattr(model, NAME, INT) (e.g. wgrad_overlap=0, dy_ring=2, bn_shifted_stats=0); recorded in config")
     ap.add_argument("--adam-foreach", dest="adam_foreach", action="store_true", help="torch.optim.Adam's default foreach path instead of fused=True")
     ap.add_argument("--force-ddp", dest="force_ddp", action="store_true", help="wrap the model in DDP even with one rank (host-overhead diagnostic)")
     ap.add_argument("--ddp-stock", dest="ddp_stock", action="store_true",

@@ -207,7 +207,7 @@ class StepEngine:
             plan.graph_state = None
             return plan.forward(x, targets, model.use_giou_loss)
         gs = plan.graph_state
-        key = (int(targets.shape[0]), bool(model.use_giou_loss))
+        key = (int(targets.shape[0]), bool(model.use_giou_loss), int(getattr(model, "wgrad_overlap", 2)), int(getattr(model, "dy_ring", 4)))
         if gs is None or gs["key"] != key:
             gs = plan.graph_state = dict(key=key, eager=0, fwd=None, bwd=None, x=torch.empty_like(x, dtype=torch.float32),
                                          tg=torch.empty(targets.shape, device=x.device, dtype=torch.float32),
@@ -536,7 +536,8 @@ class Plan:
         self.gw_numel = max(wtot, 1)
         self.gw_flat = None
         self._unpack_dev = None
-        self.dy_scratch = None
+        self.dy_ring = None                # dY buffers (BN-backward output / head gradients in fp16), rotated over the layers
+        self._wg = None                    # side stream + events of the overlapped weight-gradient launches
         self.pool_scratch = None
         max_dy = 0
         for rec in self.convs:
@@ -809,9 +810,29 @@ class Plan:
         model = self.model
         training = model.training
         dev = self.device
-        if self.dy_scratch is None:
-            self.dy_scratch = torch.zeros(self._max_dy, device=dev, dtype=torch.float16)
+        # Weight gradients on a second stream (model.wgrad_overlap): the tensor-bound cy4_conv_wgrad of layer L runs while the
+        # compute stream is in the HBM-bound BatchNorm / activation backward passes of layer L-1 (they need only dgrad_L).
+        #   0: everything on one stream;  1: wgrad_L may start as soon as dY_L exists (next to dgrad_L);
+        #   2: wgrad_L starts after dgrad_L (next to the BN passes of L-1).
+        # dY lives in a ring of model.dy_ring buffers; a slot is rewritten only after the wgrad that read it has finished.
+        mode = int(getattr(model, "wgrad_overlap", 2))
+        if self.prof is not None:
+            mode = 0                                     # per-launch event timing assumes one stream
+        ring = max(2, int(getattr(model, "dy_ring", 4))) if mode else 1
+        if self.dy_ring is None or len(self.dy_ring) != ring:
+            self.dy_ring = None
+            self.dy_ring = [torch.zeros(self._max_dy, device=dev, dtype=torch.float16) for _ in range(ring)]
+        if getattr(self, "gscale", None) is None:
             self.gscale = torch.zeros(3, device=dev, dtype=torch.float32)      # [S, 1/S, amax]
+        if mode and self._wg is None:
+            self._wg = dict(stream=torch.cuda.Stream(device=dev), fork=[torch.cuda.Event() for _ in self.convs],
+                            slot=[torch.cuda.Event() for _ in range(64)], done=torch.cuda.Event())
+        for i, rec in enumerate(self.convs):
+            rec["cidx"] = i
+        self._wg_mode = mode
+        self._dy_next = 0
+        self._slot_busy = [False] * ring
+        self._wg_open = False                            # side-stream work not yet joined by the compute stream
         g = gloss.reshape(-1)[:1].to(torch.float32).contiguous()
         self.dbn.zero_()
         for s_ in self._storages:
@@ -872,6 +893,7 @@ class Plan:
                 self._conv_backward(r, training, st, gw_flat, grads)
                 if ar_groups is not None and ind in ar_groups:
                     first, n, lo, hi = ar_groups[ind]
+                    self._join_wgrad()
                     self._unpack_range(st, first, n)
                     works.append(dist.all_reduce(gw_flat[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
             elif kind == "route":
@@ -906,6 +928,7 @@ class Plan:
                 acc = src.grad_mode()
                 self._call(L.cy4_upsample2x_bwd, out.gptr, out.ld, src.gptr, src.ld, B, Hi, Wi, src.C, acc, st)
 
+        self._join_wgrad()
         if ar_groups is None:
             _t, n_items = self._unpack_all(st)
             self._unpack_range(st, 0, n_items)
@@ -943,6 +966,15 @@ class Plan:
         """Private copies of the gradient base tensors, re-sliced into one tensor per parameter (None where no gradient)."""
         flats = [b.clone().reshape(-1) for b in self._grad_bases]
         return [None if v is None else flats[v[0]][v[1]:v[1] + v[2]].view(v[3]) for v in self._grad_layout]
+
+    def _join_wgrad(self):
+        """The compute stream waits for every weight-gradient launch issued so far on the side stream."""
+        if self._wg_mode and self._wg_open:
+            wg = self._wg
+            wg["done"].record(wg["stream"])
+            torch.cuda.current_stream().wait_event(wg["done"])
+            self._wg_open = False
+            self._slot_busy = [False] * len(self._slot_busy)
 
     def _allreduce_groups(self):
         """Gradient exchange plan: conv layers in backward order, cut into groups of roughly equal parameter
@@ -1013,12 +1045,18 @@ class Plan:
         inv_s = self.gscale[1:2]
         k, stride, pad, Cout, Cin = rec["k"], rec["stride"], rec["pad"], rec["Cout"], rec["Cin"]
         conv = rec["conv"]
-        dy = self.dy_scratch
         rec["bn_bwd_done"] = False
+        if not (rec["A"].grad_has() if rec["bn"] is not None else rec.get("has_grad")):
+            return                                       # no gradient reaches this layer
+        mode, wg = self._wg_mode, self._wg
+        slot = self._dy_next % len(self.dy_ring)
+        self._dy_next += 1
+        dy = self.dy_ring[slot]
+        if self._slot_busy[slot]:                        # the wgrad that read this buffer last must be done
+            torch.cuda.current_stream().wait_event(wg["slot"][slot])
+            self._slot_busy[slot] = False
         if rec["bn"] is not None:
             A, Y = rec["A"], rec["Y"]
-            if not A.grad_has():
-                return                                   # no gradient reaches this layer
             A.zero_unwritten()                           # e.g. only a `groups` slice of A was consumed
             c0 = rec["coff"]
             q = [self.bnq[i, c0:].data_ptr() for i in range(4)]
@@ -1036,8 +1074,6 @@ class Plan:
             rec["bn_bwd_done"] = True
             cpad = Cout
         else:
-            if not rec.get("has_grad"):
-                return
             rec["has_grad"] = False
             P = rec["P"]
             M = P.M
@@ -1049,6 +1085,9 @@ class Plan:
                 gb = torch.empty(Cout, device=self.device, dtype=torch.float32)
                 self._call(L.cy4_colsum_f32, rec["dP"].data_ptr(), P.ld, M, Cout, 1.0, gb.data_ptr(), 0, st)
                 grads[id(conv.bias)] = gb
+        side = bool(mode) and not rec["stem"]
+        if side and mode == 1:
+            wg["fork"][rec["cidx"]].record()
         # input gradient
         if not rec["stem"]:
             src = rec["src"]
@@ -1072,6 +1111,16 @@ class Plan:
         else:
             src = rec["src"]
             d = co.conv_desc(B, rec["Hi"], rec["Wi"], Cin, Cout, k, stride, pad, src.ld, ldy, co.CONV_ZERO_ACC)
-            self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), st)
+            if side:
+                if mode != 1:
+                    wg["fork"][rec["cidx"]].record()
+                ws = wg["stream"]
+                ws.wait_event(wg["fork"][rec["cidx"]])
+                self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), ws.cuda_stream)
+                wg["slot"][slot].record(ws)
+                self._slot_busy[slot] = True
+                self._wg_open = True
+            else:
+                self._call(L.cy4_conv_wgrad, ctypes.byref(d), src.ptr, dy.data_ptr(), rec["acc"].data_ptr(), st)
             # (unpacked for all layers by one launch at the end of backward)
         self._wslices.append((conv.weight, rec["woff"]))

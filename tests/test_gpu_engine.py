@@ -311,6 +311,64 @@ def test_fused_bn_backward_matches_separate_pass(cfgname, size, B):
         print("mode", mode, "worst cosine vs the separate pass", worst)
 
 
+@pytest.mark.parametrize("cfgname,size,B", [("complex_yolov4_tiny", 256, 2), ("complex_yolov4", 224, 2)])
+def test_overlapped_wgrad_stream_matches_single_stream(cfgname, size, B):
+    """model.wgrad_overlap: the weight-gradient launches on a second stream (forked after dY / after dgrad, dY in a ring of
+    buffers) against the one-stream backward, on ONE forward state (retain_graph).  Only the split-K red.add order of the
+    weight gradients may differ: everything else is the same launches on the same data, so the agreement is to fp32
+    summation order.  A ring of 2 forces the slot-reuse waits."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    strides = (16, 32) if "tiny" in cfgname else (8, 16, 32)
+    x = synth.make_bev(B, img_size=size, seed=5).cuda()
+    tg = torch.tensor(synth.make_targets(B, per_image=3, seed=2, img_size=size, strides=strides)).cuda()
+    torch.manual_seed(1)
+    model = Darknet(netdefs.cfg_path(cfgname), True).cuda().train()
+    model.wgrad_overlap = 0
+    loss, _ = model(x, tg)
+    grads = {}
+    for mode, ring in ((0, 4), (1, 2), (2, 2), (2, 4), (0, 4)):
+        model.wgrad_overlap, model.dy_ring = mode, ring
+        model.zero_grad(set_to_none=True)
+        loss.backward(retain_graph=True)
+        torch.cuda.synchronize()
+        grads.setdefault((mode, ring), []).append({n: p.grad.clone() for n, p in model.named_parameters()})
+    base, again = grads[(0, 4)]
+    noise = max(((again[n] - base[n]).abs().max() / (base[n].abs().max() + 1e-20)).item() for n in base)
+    for key in ((1, 2), (2, 2), (2, 4)):
+        g = grads[key][0]
+        worst = max(((g[n] - base[n]).abs().max() / (base[n].abs().max() + 1e-20)).item() for n in base)
+        print(cfgname, "wgrad_overlap, ring", key, "worst rel diff vs one stream", worst, "(one-stream run-to-run:", noise, ")")
+        assert worst <= max(1e-5, 4 * noise), (key, worst, noise)
+
+
+def test_overlapped_wgrad_under_cuda_graph_replay():
+    """The forked weight-gradient stream inside the captured backward graph: 6 Adam steps with CUDA-graph replay, overlap on
+    vs off, from the same initial state and inputs -- same losses to the run-to-run noise of the atomically summed statistics."""
+    from cy4 import netdefs, synth
+    from cy4.darknet import Darknet
+    x = synth.make_bev(2, img_size=256, seed=5).cuda()
+    tg = torch.tensor(synth.make_targets(2, per_image=3, seed=2, img_size=256, strides=(16, 32))).cuda()
+    runs = {}
+    for mode in (0, 2):
+        torch.manual_seed(1)
+        model = Darknet(netdefs.cfg_path("complex_yolov4_tiny"), True).cuda().train()
+        model.use_cuda_graph, model.wgrad_overlap, model.dy_ring = True, mode, 2
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        losses = []
+        for _ in range(6):
+            loss, _o = model(x, tg)
+            loss.backward()
+            opt.step(); opt.zero_grad(set_to_none=True)
+            losses.append(loss.item())
+        gs = model._engine.plan.graph_state
+        assert gs is not None and gs["bwd"] is not None          # steps 3..6 were graph replays
+        runs[mode] = losses
+    print("losses one stream", runs[0], "overlapped", runs[2])
+    for a, b in zip(runs[0], runs[2]):
+        assert abs(a - b) <= 5e-3 * abs(a), (runs[0], runs[2])
+
+
 def test_elementwise_kernels_vs_torch():
     """BN finalize/apply/backward, Mish/leaky, max pool, upsample against torch on the same fp16 data."""
     import ctypes
