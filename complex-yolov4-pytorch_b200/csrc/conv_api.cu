@@ -28,6 +28,8 @@ int g_wgrad_cluster = getenv("CY4_WGRAD_CLUSTER") ? atoi(getenv("CY4_WGRAD_CLUST
 int g_wgrad_pair = 1;       // CTA-pair weight-gradient kernel for the eligible launches (conv_wgrad.cu conv_wgrad_pair_kernel)
 int g_wgrad_wide32 = 1;     // weight gradient of 32-channel inputs: the taps of a CTA as ONE N = 32*taps MMA operand
 int g_accum_tma = 1;        // accumulate-mode outputs through TMA reduce-add stores (0: per-thread read-modify-write)
+int g_ew_carveout = 1;      // BN / activation passes ask for the max shared-memory carve-out so their blocks can sit beside a resident wgrad CTA
+int g_slab_stats = 1;       // BatchNorm statistics read off the staged fp16 output slab (0: reduce-scatter over the fp32 accumulators)
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
 // Generic launch: `a` is an NHWC tensor (C=Ca channels, ld lda) convolved with the tap table.
@@ -115,6 +117,7 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
         rc = make_tmap_2d(&tmC, g.y, (uint64_t)g.w_rows_pad, (uint64_t)p.M, (uint64_t)g.ldy * 2, cw, 32, cw * 2, 0);
         if (rc) return rc;
         p.flags |= CONV_F_TMA_OUT;
+        if (!g_slab_stats) p.flags |= CONV_F_ACC_STATS;
     }
     return pair ? launch_conv_pair(tmA, tmB, tmC, p, st) : launch_conv_tc(tmA, tmB, tmC, p, st);
 }
@@ -359,6 +362,8 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "accum_tma")) { g_accum_tma = value ? 1 : 0; return 0; }
     if (!strcmp(name, "wgrad_pair")) { g_wgrad_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv1x1_matrix")) { g_conv1x1_matrix = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "ew_carveout")) { g_ew_carveout = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "slab_stats")) { g_slab_stats = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv_pair")) { g_conv_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage
     set_error("cy4_set_option: unknown option %s", name);

@@ -151,6 +151,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int group = (warp - 2) >> 2;
         const int acc = group; uint32_t acc_phase = 0;
         int seq = 0;
+        const bool slab_st = (p.flags & (CONV_F_STATS | CONV_F_TMA_OUT | CONV_F_ACC_STATS)) == (CONV_F_STATS | CONV_F_TMA_OUT) && p.epi_mode != EPI_BWD_DZ;
         int slab_i = 0;
         for (int t = unit0; t < units; t += unit_step, ++seq) {
             if ((seq & 1) != group) continue;
@@ -200,6 +201,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         else tma_store_2d(&tmC, slab, n_blk * p.block_n + c * 32, m_blk * kPM + quarter * 32);
                         tma_store_commit();
                     }
+                    if (slab_st) {          // BatchNorm statistics of the staged slab (conv_epi.cuh slab_stats)
+                        float c0 = 0.f, c1 = 0.f;
+                        if (p.stat_shift) { const float2 cv = __ldg((const float2 *)(p.stat_shift + n0) + (lane & 15)); c0 = cv.x; c1 = cv.y; }
+                        float t1a, t1b, t2a, t2b;
+                        slab_stats(slab, lane, p.M - (m_blk * kPM + quarter * 32), c0, c1, t1a, t1b, t2a, t2b);
+                        const int col = n0 + 2 * (lane & 15), sq = lane >> 4;           // lanes 0..15 add the sums, 16..31 the squares
+                        float *dst = smem_stats ? sstat + sq * kPMaxStatCh + col : (sq ? p.ch_sqsum : p.ch_sum) + col;
+                        if (smem_stats || col < p.N) atomicAdd(dst, sq ? t2a : t1a);
+                        if (smem_stats || col + 1 < p.N) atomicAdd(dst + 1, sq ? t2b : t1b);
+                    }
                 } else if (p.flags & CONV_F_OUT_F32) {
                     if (row_ok) {
                         float *dst = (float *)p.y + orow * p.ldy + n0;
@@ -233,7 +244,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         *(uint4 *)(dst + i) = o;
                     }
                 }
-                if (p.flags & CONV_F_STATS) {
+                if ((p.flags & CONV_F_STATS) && !slab_st) {      // (no staged slab, or EPI_BWD_DZ: reduce-scatter over the accumulators)
                     float s1[32], s2[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { s1[i] = f[i]; s2[i] = f[i] * (p.epi_mode == EPI_BWD_DZ ? g[i] : f[i]); }

@@ -229,6 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int group = (warp - 2) >> 2;            // group g owns accumulator stage g
         const int acc = group; uint32_t acc_phase = 0;
         int seq = 0;
+        const bool slab_st = (p.flags & (CONV_F_STATS | CONV_F_TMA_OUT | CONV_F_ACC_STATS)) == (CONV_F_STATS | CONV_F_TMA_OUT) && p.epi_mode != EPI_BWD_DZ;
         int slab_i = 0;                               // rotating output slab of this warp
         for (int t = unit0; t < units; t += unit_step, ++seq) {
             if ((seq & 1) != group) continue;
@@ -292,6 +293,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_store_commit();
                         }
                     }
+                    if (slab_st) {          // BatchNorm statistics of the staged slab (conv_epi.cuh slab_stats)
+                        float c0 = 0.f, c1 = 0.f;
+                        if (p.stat_shift) { const float2 cv = __ldg((const float2 *)(p.stat_shift + n0) + (lane & 15)); c0 = cv.x; c1 = cv.y; }
+                        float t1a, t1b, t2a, t2b;
+                        slab_stats(slab, lane, p.M - (m_blk * kBlockM + quarter * 32), c0, c1, t1a, t1b, t2a, t2b);
+                        const int col = n0 + 2 * (lane & 15), sq = lane >> 4;           // lanes 0..15 add the sums, 16..31 the squares
+                        float *dst = smem_stats ? sstat + sq * kMaxStatCh + col : (sq ? p.ch_sqsum : p.ch_sum) + col;
+                        if (smem_stats || col < p.N) atomicAdd(dst, sq ? t2a : t1a);
+                        if (smem_stats || col + 1 < p.N) atomicAdd(dst + 1, sq ? t2b : t1b);
+                    }
                 } else if (p.flags & CONV_F_OUT_F32) {
                     if (row_ok) {
                         float *dst = (float *)p.y + orow * p.ldy + n0;
@@ -332,7 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (p.flags & CONV_F_STATS) {
+                if ((p.flags & CONV_F_STATS) && !slab_st) {      // (no staged slab, or EPI_BWD_DZ: reduce-scatter over the accumulators)
                     // Per-channel sum and sum of squares over this warp's 32 rows (rows >= M are exact
                     // zeros: their im2col pixels are out of bounds).  Reduce-scatter: lane L ends up
                     // with the totals of column L.

@@ -11,6 +11,7 @@ enum : uint32_t {
     CONV_F_STATS = 2u,     // accumulate per-channel sum / sum^2 of the fp32 accumulators
     CONV_F_ACCUM = 4u,     // y += result (fp16 read-modify-write), used by dgrad into shared grads
     CONV_F_TMA_OUT = 16u,  // internal: fp16 tile staged in swizzled smem and written with TMA stores
+    CONV_F_ACC_STATS = 32u,// internal (option slab_stats=0): statistics by reduce-scatter over the fp32 accumulators even when a slab is staged
 };
 
 // Fused epilogues (ConvKParams::epi_mode).  Both apply per-output-channel parameters and read a "side" fp16 tensor with

@@ -6,6 +6,9 @@
 // Upsample_expand in src/models/darknet2pytorch.py:22-28,64-79,180-219,256-285.
 #include <cuda_fp16.h>
 
+#include <mutex>
+#include <set>
+
 #include "common.cuh"
 #include "act.cuh"
 
@@ -134,6 +137,9 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
 #pragma unroll
             for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
         }
+        f32x2 sc2[4], sh2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { sc2[k] = f32x2_pack(sc[2 * k], sc[2 * k + 1]); sh2[k] = f32x2_pack(sh[2 * k], sh[2 * k + 1]); }
         const RowChunk rc = block_rows(M, rpi);
         for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
             uint4 vy[kUnroll], vr[kUnroll];
@@ -149,16 +155,18 @@ bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__rest
             for (int u = 0; u < kUnroll; ++u) {
                 const int64_t mm = m + u * rpi;
                 if (mm < rc.end) {
-                    float f[8], r[8];
-                    unpack8(vy[u], f);
+                    const __half2 *hy = (const __half2 *)&vy[u], *hr = (const __half2 *)&vr[u];
+                    uint4 o; __half2 *ho = (__half2 *)&o;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) f[k] = act_t<ACT>(fmaf(f[k], sc[k], sh[k]));
-                    if (RES) {
-                        unpack8(vr[u], r);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) f[k] += r[k];
+                    for (int k = 0; k < 4; ++k) {                 // channel pairs: packed fp32x2 math (act.cuh)
+                        const float2 yv = __half22float2(hy[k]);
+                        f32x2 a = act_t2<ACT>(f32x2_fma(f32x2_pack(yv.x, yv.y), sc2[k], sh2[k]));
+                        if (RES) { const float2 rv = __half22float2(hr[k]); a = f32x2_add(a, f32x2_pack(rv.x, rv.y)); }
+                        float a0, a1;
+                        f32x2_unpack(a, a0, a1);
+                        ho[k] = __floats2half2_rn(a0, a1);
                     }
-                    *(uint4 *)(out + mm * ldo + c0) = pack8(f);
+                    *(uint4 *)(out + mm * ldo + c0) = o;
                 }
             }
         }
@@ -180,14 +188,17 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, __half *__re
         const int nv = min(256, vpr - v0);
         const int rpi = 256 / nv;
         const int vec = threadIdx.x % nv, rsub = threadIdx.x / nv;
-        float a1[8], a2[8];
+        f32x2 a1[4], a2[4];                               // per channel pair: sum dz, sum dz*y
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
+        for (int k = 0; k < 4; ++k) { a1[k] = f32x2_bcast(0.f); a2[k] = a1[k]; }
         const int c0 = (v0 + vec) << 3;
         if (rsub < rpi) {
-            float sc[8], sh[8];
+            f32x2 sc2[4], sh2[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+            for (int k = 0; k < 4; ++k) {
+                sc2[k] = f32x2_pack(scale[c0 + 2 * k], scale[c0 + 2 * k + 1]);
+                sh2[k] = f32x2_pack(shift[c0 + 2 * k], shift[c0 + 2 * k + 1]);
+            }
             const RowChunk rc = block_rows(M, rpi);
             for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
                 uint4 vy[kUnroll], vg[kUnroll];
@@ -200,22 +211,29 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, __half *__re
                 for (int u = 0; u < kUnroll; ++u) {
                     const int64_t mm = m + u * rpi;
                     if (mm < rc.end) {
-                        float fy[8], fg[8];
-                        unpack8(vy[u], fy); unpack8(vg[u], fg);
+                        const __half2 *hy = (const __half2 *)&vy[u], *hg = (const __half2 *)&vg[u];
+                        uint4 o; __half2 *ho = (__half2 *)&o;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float dz = fg[k] * act_grad_t<ACT>(fmaf(fy[k], sc[k], sh[k]));
-                            fg[k] = dz;
-                            a1[k] += dz;
-                            a2[k] = fmaf(dz, fy[k], a2[k]);
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 yv = __half22float2(hy[k]), gv = __half22float2(hg[k]);
+                            const f32x2 yp = f32x2_pack(yv.x, yv.y);
+                            const f32x2 dz = f32x2_mul(f32x2_pack(gv.x, gv.y), act_grad_t2<ACT>(f32x2_fma(yp, sc2[k], sh2[k])));
+                            a1[k] = f32x2_add(a1[k], dz);
+                            a2[k] = f32x2_fma(dz, yp, a2[k]);
+                            float d0, d1;
+                            f32x2_unpack(dz, d0, d1);
+                            ho[k] = __floats2half2_rn(d0, d1);
                         }
-                        if (ACT != ACT_LINEAR) *(uint4 *)(dA + mm * ldg + c0) = pack8(fg);   // dz replaces dA (fp16)
+                        if (ACT != ACT_LINEAR) *(uint4 *)(dA + mm * ldg + c0) = o;   // dz replaces dA (fp16)
                     }
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { red[0][threadIdx.x][k] = a1[k]; red[1][threadIdx.x][k] = a2[k]; }
+        for (int k = 0; k < 4; ++k) {
+            f32x2_unpack(a1[k], red[0][threadIdx.x][2 * k], red[0][threadIdx.x][2 * k + 1]);
+            f32x2_unpack(a2[k], red[1][threadIdx.x][2 * k], red[1][threadIdx.x][2 * k + 1]);
+        }
         __syncthreads();
         for (int t = threadIdx.x; t < nv * 8; t += 256) {
             const int vv = t >> 3, kk = t & 7;
@@ -264,6 +282,12 @@ bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half 
                 Bc[k] = -sc[k] * sum_dz[c] * inv_count - A[k] * mean[c];
             } else { A[k] = 0.f; Bc[k] = 0.f; }
         }
+        f32x2 sc2[4], sh2[4], A2[4], B2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sc2[k] = f32x2_pack(sc[2 * k], sc[2 * k + 1]); sh2[k] = f32x2_pack(sh[2 * k], sh[2 * k + 1]);
+            A2[k] = f32x2_pack(A[2 * k], A[2 * k + 1]); B2[k] = f32x2_pack(Bc[2 * k], Bc[2 * k + 1]);
+        }
         const RowChunk rc = block_rows(M, rpi);
         for (int64_t m = rc.begin + rsub; m < rc.end; m += (int64_t)rpi * kUnroll) {
             uint4 vy[kUnroll], vg[kUnroll];
@@ -276,14 +300,19 @@ bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half 
             for (int u = 0; u < kUnroll; ++u) {
                 const int64_t mm = m + u * rpi;
                 if (mm < rc.end) {
-                    float fy[8], fg[8], o[8];
-                    unpack8(vy[u], fy); unpack8(vg[u], fg);
+                    const __half2 *hy = (const __half2 *)&vy[u], *hg = (const __half2 *)&vg[u];
+                    uint4 o; __half2 *ho = (__half2 *)&o;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float dz = DZ_READY ? fg[k] : fg[k] * act_grad_t<ACT>(fmaf(fy[k], sc[k], sh[k]));
-                        o[k] = fmaf(sc[k], dz, fmaf(A[k], fy[k], Bc[k]));
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 yv = __half22float2(hy[k]), gv = __half22float2(hg[k]);
+                        const f32x2 yp = f32x2_pack(yv.x, yv.y);
+                        f32x2 dz = f32x2_pack(gv.x, gv.y);
+                        if (!DZ_READY) dz = f32x2_mul(dz, act_grad_t2<ACT>(f32x2_fma(yp, sc2[k], sh2[k])));
+                        float o0, o1;
+                        f32x2_unpack(f32x2_fma(sc2[k], dz, f32x2_fma(A2[k], yp, B2[k])), o0, o1);
+                        ho[k] = __floats2half2_rn(o0, o1);
                     }
-                    *(uint4 *)(dY + mm * ldd + c0) = pack8(o);
+                    *(uint4 *)(dY + mm * ldd + c0) = o;
                 }
             }
         }
@@ -493,6 +522,22 @@ __global__ void colsum_f32_kernel(const float *__restrict__ src, int64_t lds, in
     if (threadIdx.x == 0 && c < C) out[c] = (accumulate ? out[c] : 0.f) + red[0] * scale;
 }
 
+// The BN / activation passes run NEXT TO the weight-gradient kernels of the overlapped backward (engine: model.wgrad_overlap):
+// a wgrad CTA holds ~194 KB of shared memory, so an SM that runs one is configured for the maximum shared-memory carve-out.
+// A kernel launched with the default carve-out preference (these use 0..19 KB) cannot join such an SM until it is idle; with
+// the same preference its blocks are placed beside the resident wgrad CTA (registers: 12 K + 32 K of 64 K).  L1 is irrelevant
+// to these streaming passes.  Option "ew_carveout" (conv_api.cu), read at a kernel's first launch.
+extern int g_ew_carveout;
+static void co_resident(const void *kernel)
+{
+    static std::mutex mu;
+    static std::set<const void *> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done.insert(kernel).second) return;
+    if (g_ew_carveout)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 static inline int ew_grid(int64_t total)
 {
     const int64_t need = (total + 255) / 256;
@@ -536,8 +581,11 @@ static int bn_act_fwd_launch(const void *y, int64_t ldy, const float *scale, con
     memset(&f, 0, sizeof(f));
     if (fin) f = *fin;
 #define CY4_FWD(ACT, RES, FIN)                                                                                              \
-    bn_act_fwd_kernel<ACT, RES, FIN><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, \
-                                                                                       (const __half *)residual, ldr, (__half *)out, ldo, M, C, f)
+    do {                                                                                                                    \
+        co_resident((const void *)bn_act_fwd_kernel<ACT, RES, FIN>);                                                        \
+        bn_act_fwd_kernel<ACT, RES, FIN><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, \
+                                                                                           (const __half *)residual, ldr, (__half *)out, ldo, M, C, f); \
+    } while (0)
 #define CY4_FWD_A(RES, FIN)                                                                     \
     do {                                                                                        \
         if (act == ACT_MISH) CY4_FWD(ACT_MISH, RES, FIN);                                       \
@@ -585,8 +633,11 @@ int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, con
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && M >= 0, "cy4_bn_act_bwd_reduce: bad argument");
     if (M == 0) return 0;
 #define CY4_RED(ACT)                                                                                                        \
-    bn_act_bwd_reduce_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (__half *)dA, ldg, scale, \
-                                                                                    shift, mean, rstd, M, C, sum_dz, sum_dzx)
+    do {                                                                                                                    \
+        co_resident((const void *)bn_act_bwd_reduce_kernel<ACT>);                                                           \
+        bn_act_bwd_reduce_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (__half *)dA, ldg, scale, \
+                                                                                        shift, mean, rstd, M, C, sum_dz, sum_dzx); \
+    } while (0)
     if (act == ACT_MISH) CY4_RED(ACT_MISH); else if (act == ACT_LEAKY) CY4_RED(ACT_LEAKY); else CY4_RED(ACT_LINEAR);
 #undef CY4_RED
     return cy4_launch_status("cy4_bn_act_bwd_reduce");
@@ -607,9 +658,12 @@ int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg
     CY4_CHECK_ARG(y && dA && scale && shift && mean && rstd && sum_dz && sum_dzx && dY && M >= 0, "cy4_bn_act_bwd_apply: bad argument");
     if (M == 0) return 0;
 #define CY4_APP(ACT, RDY)                                                                                                   \
-    bn_act_bwd_apply_kernel<ACT, RDY><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, \
-                                                                                        scale, shift, mean, rstd, sum_dz, sum_dzx, inv_count, \
-                                                                                        training, (__half *)dY, ldd, M, C)
+    do {                                                                                                                    \
+        co_resident((const void *)bn_act_bwd_apply_kernel<ACT, RDY>);                                                       \
+        bn_act_bwd_apply_kernel<ACT, RDY><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, \
+                                                                                            scale, shift, mean, rstd, sum_dz, sum_dzx, inv_count, \
+                                                                                            training, (__half *)dY, ldd, M, C); \
+    } while (0)
     // dz_ready: cy4_bn_act_bwd_reduce ran on the same dA buffer before (it leaves dz = dA*act'(z) there)
     if (dz_ready || act == ACT_LINEAR) CY4_APP(ACT_LINEAR, true);
     else if (act == ACT_MISH) CY4_APP(ACT_MISH, false);
@@ -623,6 +677,7 @@ int cy4_add_copy(const void *a, int64_t lda, const void *b, int64_t ldb, void *o
     EW_CHECK_C(C, "cy4_add_copy");
     CY4_CHECK_ARG(a && out && M >= 0 && (lda % 8) == 0 && (ldo % 8) == 0 && (ldb % 8) == 0, "cy4_add_copy: bad argument");
     if (M == 0) return 0;
+    co_resident((const void *)add_copy_kernel);
     add_copy_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)a, lda, (const __half *)b, ldb, (__half *)out, ldo, M, C);
     return cy4_launch_status("cy4_add_copy");
 }

@@ -364,9 +364,11 @@ def test_batched_pack_and_unpack_match_the_single_layer_kernels():
 
 
 def test_shifted_bn_statistics_have_no_cancellation():
-    """cy4_conv_fwd_stats: the BatchNorm sums taken about a per-channel shift c.  On a layer whose outputs have |mean| ~ 1000 sigma
-    the plain E[y^2] - E[y]^2 in fp32 loses the variance entirely; with c = a previous estimate of the mean it is exact to fp32
-    rounding.  (The engine passes last step's batch mean as c.)"""
+    """cy4_conv_fwd_stats: the BatchNorm sums taken about a per-channel shift c.  The statistics are those of the STORED fp16
+    tensor (the epilogue reads them off the staged output slab: what BatchNorm then normalises).  On a layer whose outputs have
+    |mean| ~ 1000 sigma the plain E[y^2] - E[y]^2 in fp32 loses the variance entirely; with c = a previous estimate of the mean
+    it is exact to fp32 rounding.  (The engine passes last step's batch mean as c.)  In a regime where fp16 storage resolves
+    sigma (|mean| ~ 25 sigma) the same statistics also match those of the fp32 convolution."""
     import ctypes
     from cy4 import _lib, convops as co
     from cy4._sigs_engine import CONV_STATS
@@ -376,26 +378,34 @@ def test_shifted_bn_statistics_have_no_cancellation():
     try:
         torch.manual_seed(3)
         B, H, Cin, Cout = 8, 76, 64, 64
-        x = (8.0 + 0.05 * torch.randn(B, H, H, Cin, device="cuda")).half()
-        w = ((1.0 + 0.2 * torch.rand(Cout, Cin, 1, 1, device="cuda")) / Cin).half()
-        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float()).double()
-        mean_ref, var_ref = ref.mean((0, 2, 3)), ref.var((0, 2, 3), unbiased=False)
-        assert (mean_ref.abs() / var_ref.sqrt()).min().item() > 500            # the regime under test
         n = B * H * H
+        w = ((1.0 + 0.2 * torch.rand(Cout, Cin, 1, 1, device="cuda")) / Cin).half()
         wp = co.pack_fprop(w.float())
-        y = torch.empty(B, H, H, Cout, device="cuda", dtype=torch.float16)
-        out = {}
-        for tag, shift in (("plain", None), ("shifted", (mean_ref + 0.01).float().contiguous())):
-            s1 = torch.zeros(Cout, device="cuda"); s2 = torch.zeros(Cout, device="cuda")
-            d = co.conv_desc(B, H, H, Cin, Cout, 1, 1, 0, Cin, Cout, CONV_STATS)
-            _lib.check(L.cy4_conv_fwd_stats(ctypes.byref(d), x.data_ptr(), wp.data_ptr(), y.data_ptr(), s1.data_ptr(), s2.data_ptr(),
-                                            shift.data_ptr() if shift is not None else None, _lib.stream()))
-            ms = s1.double() / n
-            var = s2.double() / n - ms * ms
-            mean = ms + (shift.double() if shift is not None else 0.0)
-            out[tag] = ((mean - mean_ref).abs().max().item(), ((var - var_ref).abs() / var_ref).max().item())
-        print("plain  (mean err, var rel err):", out["plain"], " shifted:", out["shifted"])
-        assert out["shifted"][0] <= 1e-4 and out["shifted"][1] <= 2e-3
-        assert out["plain"][1] > 10 * out["shifted"][1]                        # what the shift buys
+        for regime, (mu, sd) in (("extreme", (8.0, 0.05)), ("moderate", (2.0, 0.64))):
+            x = (mu + sd * torch.randn(B, H, H, Cin, device="cuda")).half()
+            ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float()).double()
+            mean_ref, var_ref = ref.mean((0, 2, 3)), ref.var((0, 2, 3), unbiased=False)
+            ratio = (mean_ref.abs() / var_ref.sqrt()).min().item()
+            assert ratio > (500 if regime == "extreme" else 15)               # the regime under test
+            y = torch.empty(B, H, H, Cout, device="cuda", dtype=torch.float16)
+            out = {}
+            for tag, shift in (("plain", None), ("shifted", (mean_ref + 0.01).float().contiguous())):
+                s1 = torch.zeros(Cout, device="cuda"); s2 = torch.zeros(Cout, device="cuda")
+                d = co.conv_desc(B, H, H, Cin, Cout, 1, 1, 0, Cin, Cout, CONV_STATS)
+                _lib.check(L.cy4_conv_fwd_stats(ctypes.byref(d), x.data_ptr(), wp.data_ptr(), y.data_ptr(), s1.data_ptr(), s2.data_ptr(),
+                                                shift.data_ptr() if shift is not None else None, _lib.stream()))
+                yd = y.double()
+                mean_y, var_y = yd.mean((0, 1, 2)), yd.var((0, 1, 2), unbiased=False)      # the stored tensor's own statistics
+                ms = s1.double() / n
+                var = s2.double() / n - ms * ms
+                mean = ms + (shift.double() if shift is not None else 0.0)
+                out[tag] = ((mean - mean_y).abs().max().item(), ((var - var_y).abs() / var_y).max().item(),
+                            ((var - var_ref).abs() / var_ref).max().item())
+            print(regime, "|mean|/sigma >= %.0f" % ratio, " plain (mean err, var rel err vs stored, vs fp32 conv):", out["plain"], " shifted:", out["shifted"])
+            assert out["shifted"][0] <= 1e-4 and out["shifted"][1] <= 1e-4
+            if regime == "extreme":
+                assert out["plain"][1] > 10 * out["shifted"][1]                  # what the shift buys
+            else:
+                assert out["shifted"][2] <= 1e-3                                 # fp16 storage resolves sigma: same as the fp32 conv's
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

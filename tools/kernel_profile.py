@@ -14,6 +14,8 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "complex_yolov4"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 torch.manual_seed(0)
 net = Darknet(netdefs.cfg_path(cfg), True).cuda().train()
+for kv in sys.argv[4:]:                  # engine knobs, e.g. wgrad_overlap=0 (per-kernel times without concurrent kernels)
+    k_, v_ = kv.split("="); setattr(net, k_, int(v_))
 opt = bench.make_optimizer(net)
 x = synth.make_bev(B).cuda(); tg = torch.tensor(synth.make_targets(B, per_image=5)).cuda()
 
