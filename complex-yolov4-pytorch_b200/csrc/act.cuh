@@ -76,12 +76,18 @@ __device__ __forceinline__ f32x2 mish_grad_f2(f32x2 z)
 }
 template <int ACT> __device__ __forceinline__ f32x2 act_t2(f32x2 z)
 {
+#ifdef CY4_SCALAR_ACT      // A/B side build (tools/gpu_call14.sh): the scalar Mish forms inside the packed passes
+    if (ACT == ACT_MISH) { float a, b; f32x2_unpack(z, a, b); return f32x2_pack(mish_f(a), mish_f(b)); }
+#endif
     if (ACT == ACT_MISH) return mish_f2(z);
     if (ACT == ACT_LEAKY) { float a, b; f32x2_unpack(z, a, b); return f32x2_pack(fmaxf(a, 0.1f * a), fmaxf(b, 0.1f * b)); }
     return z;
 }
 template <int ACT> __device__ __forceinline__ f32x2 act_grad_t2(f32x2 z)
 {
+#ifdef CY4_SCALAR_ACT
+    if (ACT == ACT_MISH) { float a, b; f32x2_unpack(z, a, b); return f32x2_pack(mish_grad_f(a), mish_grad_f(b)); }
+#endif
     if (ACT == ACT_MISH) return mish_grad_f2(z);
     if (ACT == ACT_LEAKY) { float a, b; f32x2_unpack(z, a, b); return f32x2_pack(a > 0.f ? 1.f : 0.1f, b > 0.f ? 1.f : 0.1f); }
     return f32x2_bcast(1.f);

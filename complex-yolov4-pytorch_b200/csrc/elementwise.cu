@@ -522,11 +522,10 @@ __global__ void colsum_f32_kernel(const float *__restrict__ src, int64_t lds, in
     if (threadIdx.x == 0 && c < C) out[c] = (accumulate ? out[c] : 0.f) + red[0] * scale;
 }
 
-// The BN / activation passes run NEXT TO the weight-gradient kernels of the overlapped backward (engine: model.wgrad_overlap):
-// a wgrad CTA holds ~194 KB of shared memory, so an SM that runs one is configured for the maximum shared-memory carve-out.
-// A kernel launched with the default carve-out preference (these use 0..19 KB) cannot join such an SM until it is idle; with
-// the same preference its blocks are placed beside the resident wgrad CTA (registers: 12 K + 32 K of 64 K).  L1 is irrelevant
-// to these streaming passes.  Option "ew_carveout" (conv_api.cu), read at a kernel's first launch.
+// Experiment kept as an option ("ew_carveout", default 0, read at a kernel's first launch): ask for the maximum shared-memory
+// carve-out so that blocks of these passes can be placed beside a resident weight-gradient CTA (~194 KB of shared memory) of
+// the overlapped backward.  Measured on B200 (profiles/r2_overlap_ab.md): 0.7 ms per step SLOWER -- bn_act_bwd_apply alone
+// 3.96 -> 4.83 ms: the streaming passes do use their L1 -- and the overlap gains nothing from it.
 extern int g_ew_carveout;
 static void co_resident(const void *kernel)
 {

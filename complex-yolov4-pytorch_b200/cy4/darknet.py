@@ -176,6 +176,7 @@ class Darknet(nn.Module):
         self.sync_outputs = False       # True: the CPU detections are complete when forward returns (training)
         self.use_cuda_graph = False     # True: after 2 eager steps the fwd / bwd launch sequences are replayed as CUDA graphs
         self.wgrad_overlap = 2          # backward: weight gradients on a second stream, next to the HBM-bound BN passes (0: one stream; 1: fork before dgrad)
+        self.wgrad_priority = 0         # CUDA stream priority of that second stream (-1: its kernels are placed before the compute stream's)
         self.dy_ring = 4                # number of dY buffers the overlapped backward rotates through
         self.bn_shifted_stats = True    # training: BN statistics summed about the previous step's batch mean (no E[y^2]-E[y]^2 cancellation)
         self.engine_allreduce = False   # True (set by models.model_utils.make_data_parallel): the engine averages gradients over the ranks

@@ -207,7 +207,8 @@ class StepEngine:
             plan.graph_state = None
             return plan.forward(x, targets, model.use_giou_loss)
         gs = plan.graph_state
-        key = (int(targets.shape[0]), bool(model.use_giou_loss), int(getattr(model, "wgrad_overlap", 2)), int(getattr(model, "dy_ring", 4)))
+        key = (int(targets.shape[0]), bool(model.use_giou_loss), int(getattr(model, "wgrad_overlap", 2)), int(getattr(model, "dy_ring", 4)),
+               int(getattr(model, "wgrad_priority", 0)))
         if gs is None or gs["key"] != key:
             gs = plan.graph_state = dict(key=key, eager=0, fwd=None, bwd=None, x=torch.empty_like(x, dtype=torch.float32),
                                          tg=torch.empty(targets.shape, device=x.device, dtype=torch.float32),
@@ -824,8 +825,12 @@ class Plan:
             self.dy_ring = [torch.zeros(self._max_dy, device=dev, dtype=torch.float16) for _ in range(ring)]
         if getattr(self, "gscale", None) is None:
             self.gscale = torch.zeros(3, device=dev, dtype=torch.float32)      # [S, 1/S, amax]
-        if mode and self._wg is None:
-            self._wg = dict(stream=torch.cuda.Stream(device=dev), fork=[torch.cuda.Event() for _ in self.convs],
+        prio = int(getattr(model, "wgrad_priority", 0))
+        if mode and (self._wg is None or self._wg["prio"] != prio):
+            # priority -1: when a weight-gradient kernel and a BN pass become ready together, the wgrad CTAs (one per SM, ~194 KB of
+            # shared memory) are placed first and the pass's blocks fill in beside them; with equal priorities whichever kernel was
+            # launched first takes every SM (3 resident BN blocks leave no registers for a wgrad CTA) and the two serialise.
+            self._wg = dict(prio=prio, stream=torch.cuda.Stream(device=dev, priority=prio), fork=[torch.cuda.Event() for _ in self.convs],
                             slot=[torch.cuda.Event() for _ in range(64)], done=torch.cuda.Event())
         for i, rec in enumerate(self.convs):
             rec["cidx"] = i

@@ -155,8 +155,8 @@ typedef struct cy4_conv_desc {
  * "accum_tma" (0|1, default 1): CY4_CONV_ACCUM outputs through TMA reduce-add stores instead of per-thread read-modify-write;
  * "wgrad_pair" (0|1, default 1): CTA-pair weight-gradient kernel for layers with Cout % 256 == 0 and a 128/256-channel X tile;
  * "conv_pair" (0|1, default 1): CTA-pair (tcgen05 cta_group::2, 256-row tiles) kernel for the eligible conv launches;
- * "ew_carveout" (0|1, default 1; read at a kernel's first launch): the BN / activation passes prefer the maximum shared-memory
- *   carve-out, so their blocks can be placed beside a resident weight-gradient CTA (overlapped backward);
+ * "ew_carveout" (0|1, default 0; read at a kernel's first launch): 1 = the BN / activation passes prefer the maximum shared-memory
+ *   carve-out (experiment: measured slower, kept for the record);
  * "slab_stats" (0|1, default 1): CY4_CONV_STATS sums are read off the staged fp16 output slab (the statistics of the STORED tensor,
  *   ~100 instructions per 32x32 slab) instead of a shuffle reduce-scatter over the fp32 accumulators (~400, a dependent chain);
  * "debug": bottleneck experiments, honoured only by -DCY4_PROBE side builds (tools/probe_pipeline.py). */

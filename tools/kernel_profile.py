@@ -14,8 +14,13 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "complex_yolov4"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 torch.manual_seed(0)
 net = Darknet(netdefs.cfg_path(cfg), True).cuda().train()
-for kv in sys.argv[4:]:                  # engine knobs, e.g. wgrad_overlap=0 (per-kernel times without concurrent kernels)
-    k_, v_ = kv.split("="); setattr(net, k_, int(v_))
+for kv in sys.argv[4:]:                  # engine knobs, e.g. wgrad_overlap=0 (per-kernel times without concurrent kernels); opt:NAME=INT -> cy4_set_option
+    k_, v_ = kv.split("=")
+    if k_.startswith("opt:"):
+        from cy4 import _lib
+        _lib.check(_lib.lib().cy4_set_option(k_[4:].encode(), int(v_)), kv)
+    else:
+        setattr(net, k_, int(v_))
 opt = bench.make_optimizer(net)
 x = synth.make_bev(B).cuda(); tg = torch.tensor(synth.make_targets(B, per_image=5)).cuda()
 
@@ -34,7 +39,10 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 tot = 0.0
 for e in prof.events():
     if e.device_type is not None and "cuda" in str(e.device_type).lower():
-        name = re.sub(r"<.*", "", e.name.split("(")[0]).replace("void ", "").replace("cy4::", "")[-56:]
+        name = e.name.split("(")[0].replace("void ", "").replace("cy4::", "")
+        if not name.startswith("bn_act"):                  # (keep the <activation, ...> template arguments of the BN passes)
+            name = re.sub(r"<.*", "", name)
+        name = name[-56:]
         agg[name][0] += 1; agg[name][1] += e.device_time / 1e3 if hasattr(e, "device_time") else e.cuda_time / 1e3
         tot += e.device_time / 1e3 if hasattr(e, "device_time") else e.cuda_time / 1e3
 seq = [(re.sub(r"<.*", "", e.name.split("(")[0]).replace("void ", "").replace("cy4::", ""), (e.device_time if hasattr(e, "device_time") else e.cuda_time))
