@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const ConvKParams p)
 {
+    pdl_trigger();                           // the next kernel of the stream may start its own set-up (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nst = p.stages;
@@ -85,6 +86,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+    pdl_wait();                              // set-up done; from here on global memory written by the preceding kernels is touched
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -330,11 +332,11 @@ int launch_conv_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUten
     cfg.blockDim = dim3(kPThreads);
     cfg.dynamicSmemBytes = kPSmem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_launch_attr(attr, 1);
     CY4_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel, tmA, tmB, tmC, p));
     return cy4_launch_status("conv_pair_kernel");
 }

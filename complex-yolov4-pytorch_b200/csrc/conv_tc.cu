@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvKParams p)
 {
+    pdl_trigger();                           // the next kernel of the stream may start its own set-up (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // The TMA -> MMA round trip is ~1.5-2 us; a slot only holds 12..48 KB, so narrow / small-K layers need
@@ -125,6 +126,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (cs > 1) cluster_sync_all();          // peers' barriers are initialised before any multicast targets them
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+    pdl_wait();                              // set-up done; from here on global memory written by the preceding kernels is touched
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -495,11 +497,11 @@ int launch_conv_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtenso
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = cs > 1 ? 1 : 0;
+    cfg.numAttrs = pdl_launch_attr(attr, cs > 1 ? 1 : 0);
     CY4_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, tmA, tmB, tmC, p));
     return cy4_launch_status("conv_tc_kernel");
 }

@@ -68,6 +68,7 @@ struct WCtl {
 __global__ void __launch_bounds__(kWThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WgradParams p)
 {
+    pdl_trigger();                           // the next kernel of the stream may start its own set-up (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
@@ -102,6 +103,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     if (cs > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+    pdl_wait();                              // set-up done; from here on global memory written by the preceding kernels is touched
 
     if (nkb > 0) {
         if (warp == 0) {
@@ -234,6 +236,7 @@ struct WPCtl {
 __global__ void __launch_bounds__(kWThreads, 1)
 conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WgradParams p)
 {
+    pdl_trigger();                           // the next kernel of the stream may start its own set-up (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
@@ -266,6 +269,7 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+    pdl_wait();                              // set-up done; from here on global memory written by the preceding kernels is touched
 
     if (nkb > 0) {
         if (warp == 0) {
@@ -444,10 +448,10 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
         pc.blockDim = dim3(kWThreads);
         pc.dynamicSmemBytes = kWPSmem;
         pc.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute pa[1];
+        cudaLaunchAttribute pa[2];
         pa[0].id = cudaLaunchAttributeClusterDimension;
         pa[0].val.clusterDim.x = 2; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
-        pc.attrs = pa; pc.numAttrs = 1;
+        pc.attrs = pa; pc.numAttrs = pdl_launch_attr(pa, 1);
         CY4_CUDA(cudaLaunchKernelEx(&pc, conv_wgrad_pair_kernel, tmDy, tmX, p));
         return cy4_launch_status("cy4_conv_wgrad (pair)");
     }
@@ -458,11 +462,11 @@ extern "C" int cy4_conv_wgrad(const cy4_conv_desc *d, const void *x, const void 
     cfg.blockDim = dim3(kWThreads);
     cfg.dynamicSmemBytes = kWSmem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = p.cluster > 1 ? 1 : 0;
+    cfg.numAttrs = pdl_launch_attr(attr, p.cluster > 1 ? 1 : 0);
     CY4_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tmDy, tmX, p));
     return cy4_launch_status("cy4_conv_wgrad");
 }

@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(256, 3)
 bn_act_fwd_kernel(const __half *__restrict__ y, int64_t ldy, const float *__restrict__ scale, const float *__restrict__ shift,
                   const __half *__restrict__ res, int64_t ldr, __half *__restrict__ out, int64_t ldo, int64_t M, int C, const BnFin fin)
 {
+    pdl_trigger();
+    pdl_wait();                              // (reads per-channel data the preceding kernel produced right away)
     const int vpr = C >> 3;
     for (int v0 = 0; v0 < vpr; v0 += 256) {
         const int nv = min(256, vpr - v0);
@@ -182,6 +184,8 @@ bn_act_bwd_reduce_kernel(const __half *__restrict__ y, int64_t ldy, __half *__re
                          const float *__restrict__ rstd, int64_t M, int C, float *__restrict__ sum_dz,
                          float *__restrict__ sum_dzx)
 {
+    pdl_trigger();
+    pdl_wait();                              // (reads per-channel data the preceding kernel produced right away)
     const int vpr = C >> 3;
     __shared__ float red[2][256][8 + 1];
     for (int v0 = 0; v0 < vpr; v0 += 256) {
@@ -265,6 +269,8 @@ bn_act_bwd_apply_kernel(const __half *__restrict__ y, int64_t ldy, const __half 
                         const float *__restrict__ rstd, const float *__restrict__ sum_dz, const float *__restrict__ sum_dzx,
                         float inv_count, int training, __half *__restrict__ dY, int64_t ldd, int64_t M, int C)
 {
+    pdl_trigger();
+    pdl_wait();                              // (reads per-channel data the preceding kernel produced right away)
     const int vpr = C >> 3;
     for (int v0 = 0; v0 < vpr; v0 += 256) {
         const int nv = min(256, vpr - v0);
@@ -324,6 +330,8 @@ __global__ void __launch_bounds__(256)
 add_copy_kernel(const __half *__restrict__ a, int64_t lda, const __half *__restrict__ b, int64_t ldb, __half *__restrict__ out,
                 int64_t ldo, int64_t M, int C)
 {
+    pdl_trigger();
+    pdl_wait();
     const int vpr = C >> 3;
     const int64_t total = M * vpr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -582,8 +590,8 @@ static int bn_act_fwd_launch(const void *y, int64_t ldy, const float *scale, con
 #define CY4_FWD(ACT, RES, FIN)                                                                                              \
     do {                                                                                                                    \
         co_resident((const void *)bn_act_fwd_kernel<ACT, RES, FIN>);                                                        \
-        bn_act_fwd_kernel<ACT, RES, FIN><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, scale, shift, \
-                                                                                           (const __half *)residual, ldr, (__half *)out, ldo, M, C, f); \
+        launch_pdl(bn_act_fwd_kernel<ACT, RES, FIN>, col_grid(M, C), 256, (cudaStream_t)stream, (const __half *)y, ldy, scale, shift, \
+                   (const __half *)residual, ldr, (__half *)out, ldo, M, C, f);                                                 \
     } while (0)
 #define CY4_FWD_A(RES, FIN)                                                                     \
     do {                                                                                        \
@@ -634,8 +642,8 @@ int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, con
 #define CY4_RED(ACT)                                                                                                        \
     do {                                                                                                                    \
         co_resident((const void *)bn_act_bwd_reduce_kernel<ACT>);                                                           \
-        bn_act_bwd_reduce_kernel<ACT><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (__half *)dA, ldg, scale, \
-                                                                                        shift, mean, rstd, M, C, sum_dz, sum_dzx); \
+        launch_pdl(bn_act_bwd_reduce_kernel<ACT>, col_grid(M, C), 256, (cudaStream_t)stream, (const __half *)y, ldy, (__half *)dA, ldg, scale, \
+                   shift, mean, rstd, M, C, sum_dz, sum_dzx);                                                                   \
     } while (0)
     if (act == ACT_MISH) CY4_RED(ACT_MISH); else if (act == ACT_LEAKY) CY4_RED(ACT_LEAKY); else CY4_RED(ACT_LINEAR);
 #undef CY4_RED
@@ -659,9 +667,8 @@ int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg
 #define CY4_APP(ACT, RDY)                                                                                                   \
     do {                                                                                                                    \
         co_resident((const void *)bn_act_bwd_apply_kernel<ACT, RDY>);                                                       \
-        bn_act_bwd_apply_kernel<ACT, RDY><<<col_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __half *)y, ldy, (const __half *)dA, ldg, \
-                                                                                            scale, shift, mean, rstd, sum_dz, sum_dzx, inv_count, \
-                                                                                            training, (__half *)dY, ldd, M, C); \
+        launch_pdl(bn_act_bwd_apply_kernel<ACT, RDY>, col_grid(M, C), 256, (cudaStream_t)stream, (const __half *)y, ldy, (const __half *)dA, ldg, \
+                   scale, shift, mean, rstd, sum_dz, sum_dzx, inv_count, training, (__half *)dY, ldd, M, C);                    \
     } while (0)
     // dz_ready: cy4_bn_act_bwd_reduce ran on the same dA buffer before (it leaves dz = dA*act'(z) there)
     if (dz_ready || act == ACT_LINEAR) CY4_APP(ACT_LINEAR, true);
@@ -677,7 +684,7 @@ int cy4_add_copy(const void *a, int64_t lda, const void *b, int64_t ldb, void *o
     CY4_CHECK_ARG(a && out && M >= 0 && (lda % 8) == 0 && (ldo % 8) == 0 && (ldb % 8) == 0, "cy4_add_copy: bad argument");
     if (M == 0) return 0;
     co_resident((const void *)add_copy_kernel);
-    add_copy_kernel<<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)a, lda, (const __half *)b, ldb, (__half *)out, ldo, M, C);
+    launch_pdl(add_copy_kernel, ew_grid(M * (C / 8)), 256, (cudaStream_t)stream, (const __half *)a, lda, (const __half *)b, ldb, (__half *)out, ldo, M, C);
     return cy4_launch_status("cy4_add_copy");
 }
 

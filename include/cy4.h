@@ -155,6 +155,9 @@ typedef struct cy4_conv_desc {
  * "accum_tma" (0|1, default 1): CY4_CONV_ACCUM outputs through TMA reduce-add stores instead of per-thread read-modify-write;
  * "wgrad_pair" (0|1, default 1): CTA-pair weight-gradient kernel for layers with Cout % 256 == 0 and a 128/256-channel X tile;
  * "conv_pair" (0|1, default 1): CTA-pair (tcgen05 cta_group::2, 256-row tiles) kernel for the eligible conv launches;
+ * "pdl" (0|1; environment CY4_PDL sets the initial value): programmatic dependent launch of the tensor-core and BN / activation
+ *   kernels -- each calls griddepcontrol.launch_dependents first thing and griddepcontrol.wait before its first global access,
+ *   so the next kernel's blocks are placed and set up (barriers, TMEM, descriptors) while the previous grid drains;
  * "ew_carveout" (0|1, default 0; read at a kernel's first launch): 1 = the BN / activation passes prefer the maximum shared-memory
  *   carve-out (experiment: measured slower, kept for the record);
  * "slab_stats" (0|1, default 1): CY4_CONV_STATS sums are read off the staged fp16 output slab (the statistics of the STORED tensor,

@@ -369,6 +369,58 @@ def test_overlapped_wgrad_under_cuda_graph_replay():
         assert abs(a - b) <= 5e-3 * abs(a), (runs[0], runs[2])
 
 
+def test_programmatic_dependent_launch_gives_the_same_step():
+    """Option "pdl": the hot kernels launched with the programmatic-stream-serialization permission (each triggers its dependents
+    first thing and waits for its predecessors before the first global access).  Eager launches and CUDA-graph replay, against
+    the plain launches, from the same initial state: same losses over 6 Adam steps (to the run-to-run noise of the atomically
+    summed statistics), same gradients on a shared forward (one-stream backward, so only the launch mode differs)."""
+    from cy4 import _lib, netdefs, synth
+    from cy4.darknet import Darknet
+    L = _lib.lib()
+    x = synth.make_bev(2, img_size=256, seed=5).cuda()
+    tg = torch.tensor(synth.make_targets(2, per_image=3, seed=2, img_size=256, strides=(16, 32))).cuda()
+    runs = {}
+    try:
+        for pdl, graph in ((0, False), (1, False), (1, True)):
+            _lib.check(L.cy4_set_option(b"pdl", pdl))
+            torch.manual_seed(1)
+            model = Darknet(netdefs.cfg_path("complex_yolov4_tiny"), True).cuda().train()
+            model.use_cuda_graph = graph
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+            losses = []
+            for _ in range(6):
+                loss, _o = model(x, tg)
+                loss.backward()
+                opt.step(); opt.zero_grad(set_to_none=True)
+                losses.append(loss.item())
+            runs[(pdl, graph)] = losses
+        print("losses plain", runs[(0, False)], "pdl eager", runs[(1, False)], "pdl graph", runs[(1, True)])
+        for key in ((1, False), (1, True)):
+            for a, b in zip(runs[(0, False)], runs[key]):
+                assert abs(a - b) <= 5e-3 * abs(a), (key, runs)
+        # gradients on ONE forward state
+        torch.manual_seed(1)
+        model = Darknet(netdefs.cfg_path("complex_yolov4"), True).cuda().train()
+        model.wgrad_overlap = 0
+        xb = synth.make_bev(2, img_size=224, seed=5).cuda()
+        tb = torch.tensor(synth.make_targets(2, per_image=3, seed=2, img_size=224, strides=(8, 16, 32))).cuda()
+        _lib.check(L.cy4_set_option(b"pdl", 0))
+        loss, _ = model(xb, tb)
+        grads = []
+        for pdl in (0, 0, 1):
+            _lib.check(L.cy4_set_option(b"pdl", pdl))
+            model.zero_grad(set_to_none=True)
+            loss.backward(retain_graph=True)
+            torch.cuda.synchronize()
+            grads.append({n: p.grad.clone() for n, p in model.named_parameters()})
+        rel = lambda g, h: max(((g[n] - h[n]).abs().max() / (h[n].abs().max() + 1e-20)).item() for n in h)
+        noise, diff = rel(grads[1], grads[0]), rel(grads[2], grads[0])
+        print("complex_yolov4 backward: pdl vs plain", diff, "plain run-to-run", noise)
+        assert diff <= max(1e-5, 4 * noise)
+    finally:
+        _lib.check(L.cy4_set_option(b"pdl", int(__import__("os").environ.get("CY4_PDL", "0"))))
+
+
 def test_elementwise_kernels_vs_torch():
     """BN finalize/apply/backward, Mish/leaky, max pool, upsample against torch on the same fp16 data."""
     import ctypes
