@@ -29,7 +29,7 @@ int g_wgrad_pair = 1;       // CTA-pair weight-gradient kernel for the eligible 
 int g_wgrad_wide32 = 1;     // weight gradient of 32-channel inputs: the taps of a CTA as ONE N = 32*taps MMA operand
 int g_accum_tma = 1;        // accumulate-mode outputs through TMA reduce-add stores (0: per-thread read-modify-write)
 int g_pdl = getenv("CY4_PDL") ? atoi(getenv("CY4_PDL")) : 0;   // programmatic dependent launch of the hot kernels (common.cuh)
-int g_ew_blocks_per_sm = 6;  // grid cap of the column-owner BN / activation passes, in blocks per SM
+int g_ew_fwd_bpsm = 3, g_ew_bwd_bpsm = 2;   // grid caps of the BN / activation passes in blocks per SM (one resident wave each)
 int g_ew_carveout = 0;      // 1: BN / activation passes ask for the max shared-memory carve-out (measured: -0.7 ms/step WORSE, the passes want their L1)
 int g_slab_stats = 1;       // BatchNorm statistics read off the staged fp16 output slab (0: reduce-scatter over the fp32 accumulators)
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
@@ -365,7 +365,8 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "wgrad_pair")) { g_wgrad_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv1x1_matrix")) { g_conv1x1_matrix = value ? 1 : 0; return 0; }
     if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "ew_blocks_per_sm")) { CY4_CHECK_ARG(value >= 1 && value <= 32, "ew_blocks_per_sm must be in 1..32"); g_ew_blocks_per_sm = value; return 0; }
+    if (!strcmp(name, "ew_fwd_blocks_per_sm")) { CY4_CHECK_ARG(value >= 1 && value <= 32, "ew_fwd_blocks_per_sm must be in 1..32"); g_ew_fwd_bpsm = value; return 0; }
+    if (!strcmp(name, "ew_bwd_blocks_per_sm")) { CY4_CHECK_ARG(value >= 1 && value <= 32, "ew_bwd_blocks_per_sm must be in 1..32"); g_ew_bwd_bpsm = value; return 0; }
     if (!strcmp(name, "ew_carveout")) { g_ew_carveout = value ? 1 : 0; return 0; }
     if (!strcmp(name, "slab_stats")) { g_slab_stats = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv_pair")) { g_conv_pair = value ? 1 : 0; return 0; }

@@ -430,6 +430,70 @@ maxpool_fwd_kernel(const __half *__restrict__ in, int64_t ldi, __half *__restric
         *(uint4 *)(out + (((int64_t)b * Ho + oh) * Wo + ow) * ldo + c0) = pack8(best);
     }
 }
+// Forward that also records, per output element, WHICH window element was the first maximum (torch's scan order) as the
+// window offset dy * k + dx in one byte: the backward pass then routes gradients without re-scanning the k x k windows
+// (169 16-byte loads per output vector for the 13 x 13 SPP pool).
+__global__ void __launch_bounds__(256)
+maxpool_fwd_idx_kernel(const __half *__restrict__ in, int64_t ldi, __half *__restrict__ out, int64_t ldo, uint8_t *__restrict__ argmax,
+                       int B, int H, int W, int C, int k, int s, int pad, int Ho, int Wo)
+{
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * Ho * Wo * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
+        const int ow = (int)(r % Wo); r /= Wo;
+        const int oh = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        float best[8], t[8]; int bpos[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bpos[q] = -1; }
+        for (int dy = 0; dy < k; ++dy) {
+            const int h = oh * s - pad + dy;
+            if (h < 0 || h >= H) continue;
+            for (int dx = 0; dx < k; ++dx) {
+                const int w = ow * s - pad + dx;
+                if (w < 0 || w >= W) continue;
+                unpack8(*(const uint4 *)(in + (((int64_t)b * H + h) * W + w) * ldi + c0), t);
+                const int pos = dy * k + dx;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (t[q] > best[q] || bpos[q] < 0) { best[q] = t[q]; bpos[q] = pos; }
+            }
+        }
+        const int64_t o = ((int64_t)b * Ho + oh) * Wo + ow;
+        *(uint4 *)(out + o * ldo + c0) = pack8(best);
+        uint2 pk;
+        pk.x = (uint32_t)(bpos[0] & 255) | ((uint32_t)(bpos[1] & 255) << 8) | ((uint32_t)(bpos[2] & 255) << 16) | ((uint32_t)(bpos[3] & 255) << 24);
+        pk.y = (uint32_t)(bpos[4] & 255) | ((uint32_t)(bpos[5] & 255) << 8) | ((uint32_t)(bpos[6] & 255) << 16) | ((uint32_t)(bpos[7] & 255) << 24);
+        *(uint2 *)(argmax + o * C + c0) = pk;
+    }
+}
+__global__ void __launch_bounds__(256)
+maxpool_bwd_idx_kernel(const uint8_t *__restrict__ argmax, const __half *__restrict__ gout, int64_t ldo, float *__restrict__ gscratch,
+                       int B, int H, int W, int C, int k, int s, int pad, int Ho, int Wo)
+{
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * Ho * Wo * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
+        const int ow = (int)(r % Wo); r /= Wo;
+        const int oh = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const int64_t o = ((int64_t)b * Ho + oh) * Wo + ow;
+        const uint2 pk = *(const uint2 *)(argmax + o * C + c0);
+        float g[8];
+        unpack8(*(const uint4 *)(gout + o * ldo + c0), g);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int pos = (int)(((q < 4 ? pk.x : pk.y) >> ((q & 3) * 8)) & 255u);
+            const int dy = pos / k, dx = pos - dy * k;
+            const int h = oh * s - pad + dy, w = ow * s - pad + dx;
+            atomicAdd(gscratch + (((int64_t)b * H + h) * W + w) * C + c0 + q, g[q]);
+        }
+    }
+}
 // gradient: each output pixel routes its gradient to the FIRST maximal element of its window
 // (torch's scan order), accumulated in an fp32 scratch [B,H,W,C] with atomics.
 __global__ void __launch_bounds__(256)
@@ -574,13 +638,16 @@ static inline int ew_grid(int64_t total)
 
 // grid for the column-owner kernels: enough blocks for ~4 resident 256-thread blocks per SM, but
 // no more than one block per kUnroll row groups
-extern int g_ew_blocks_per_sm;       // conv_api.cu, option "ew_blocks_per_sm"
-static inline int col_grid(int64_t M, int C)
+// Grid cap in blocks per SM: ONE resident wave (3 blocks of the forward pass, 2 of the backward passes fit an SM) -- measured
+// on B200 (profiles/r2_overlap_ab.md): 6 blocks per SM (two waves, each block re-deriving its per-channel constants) costs
+// 0.2 ms per step in the forward passes and 0.85 ms in the backward ones.  Options "ew_fwd_blocks_per_sm" / "ew_bwd_blocks_per_sm".
+extern int g_ew_fwd_bpsm, g_ew_bwd_bpsm;
+static inline int col_grid(int64_t M, int C, int blocks_per_sm)
 {
     const int vpr = C / 8;
     const int rpi = std::max(1, 256 / std::min(vpr, 256));
     const int64_t groups = (M + (int64_t)rpi * kUnroll - 1) / ((int64_t)rpi * kUnroll);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)sm_count() * g_ew_blocks_per_sm));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)sm_count() * blocks_per_sm));
 }
 
 }  // namespace cy4
@@ -612,7 +679,7 @@ static int bn_act_fwd_launch(const void *y, int64_t ldy, const float *scale, con
 #define CY4_FWD(ACT, RES, FIN)                                                                                              \
     do {                                                                                                                    \
         co_resident((const void *)bn_act_fwd_kernel<ACT, RES, FIN>);                                                        \
-        launch_pdl(bn_act_fwd_kernel<ACT, RES, FIN>, col_grid(M, C), 256, (cudaStream_t)stream, (const __half *)y, ldy, scale, shift, \
+        launch_pdl(bn_act_fwd_kernel<ACT, RES, FIN>, col_grid(M, C, g_ew_fwd_bpsm), 256, (cudaStream_t)stream, (const __half *)y, ldy, scale, shift, \
                    (const __half *)residual, ldr, (__half *)out, ldo, M, C, f);                                                 \
     } while (0)
 #define CY4_FWD_A(RES, FIN)                                                                     \
@@ -664,7 +731,7 @@ int cy4_bn_act_bwd_reduce(const void *y, int64_t ldy, void *dA, int64_t ldg, con
 #define CY4_RED(ACT)                                                                                                        \
     do {                                                                                                                    \
         co_resident((const void *)bn_act_bwd_reduce_kernel<ACT>);                                                           \
-        launch_pdl(bn_act_bwd_reduce_kernel<ACT>, col_grid(M, C), 256, (cudaStream_t)stream, (const __half *)y, ldy, (__half *)dA, ldg, scale, \
+        launch_pdl(bn_act_bwd_reduce_kernel<ACT>, col_grid(M, C, g_ew_bwd_bpsm), 256, (cudaStream_t)stream, (const __half *)y, ldy, (__half *)dA, ldg, scale, \
                    shift, mean, rstd, M, C, sum_dz, sum_dzx);                                                                   \
     } while (0)
     if (act == ACT_MISH) CY4_RED(ACT_MISH); else if (act == ACT_LEAKY) CY4_RED(ACT_LEAKY); else CY4_RED(ACT_LINEAR);
@@ -689,7 +756,7 @@ int cy4_bn_act_bwd_apply(const void *y, int64_t ldy, const void *dA, int64_t ldg
 #define CY4_APP(ACT, RDY)                                                                                                   \
     do {                                                                                                                    \
         co_resident((const void *)bn_act_bwd_apply_kernel<ACT, RDY>);                                                       \
-        launch_pdl(bn_act_bwd_apply_kernel<ACT, RDY>, col_grid(M, C), 256, (cudaStream_t)stream, (const __half *)y, ldy, (const __half *)dA, ldg, \
+        launch_pdl(bn_act_bwd_apply_kernel<ACT, RDY>, col_grid(M, C, g_ew_bwd_bpsm), 256, (cudaStream_t)stream, (const __half *)y, ldy, (const __half *)dA, ldg, \
                    scale, shift, mean, rstd, sum_dz, sum_dzx, inv_count, training, (__half *)dY, ldd, M, C);                    \
     } while (0)
     // dz_ready: cy4_bn_act_bwd_reduce ran on the same dA buffer before (it leaves dz = dA*act'(z) there)
@@ -744,6 +811,28 @@ int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, 
     maxpool_bwd_kernel<<<ew_grid((int64_t)B * Ho * Wo * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (const __half *)gout, ldo, gscratch,
                                                                                             B, H, W, C, k, stride, pad, Ho, Wo);
     return cy4_launch_status("cy4_maxpool_bwd");
+}
+
+int cy4_maxpool_fwd_idx(const void *in, int64_t ldi, void *out, int64_t ldo, void *argmax, int B, int H, int W, int C, int k, int stride,
+                        int pad, void *stream)
+{
+    EW_CHECK_C(C, "cy4_maxpool_fwd_idx");
+    CY4_CHECK_ARG(in && out && argmax && k > 0 && k * k <= 255 && stride > 0, "cy4_maxpool_fwd_idx: bad argument (window of at most 255 elements)");
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    maxpool_fwd_idx_kernel<<<ew_grid((int64_t)B * Ho * Wo * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (__half *)out, ldo,
+                                                                                                (uint8_t *)argmax, B, H, W, C, k, stride, pad, Ho, Wo);
+    return cy4_launch_status("cy4_maxpool_fwd_idx");
+}
+
+int cy4_maxpool_bwd_idx(const void *argmax, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C, int k, int stride,
+                        int pad, void *stream)
+{
+    EW_CHECK_C(C, "cy4_maxpool_bwd_idx");
+    CY4_CHECK_ARG(argmax && gout && gscratch && k > 0 && k * k <= 255 && stride > 0, "cy4_maxpool_bwd_idx: bad argument");
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    maxpool_bwd_idx_kernel<<<ew_grid((int64_t)B * Ho * Wo * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const uint8_t *)argmax, (const __half *)gout, ldo,
+                                                                                                gscratch, B, H, W, C, k, stride, pad, Ho, Wo);
+    return cy4_launch_status("cy4_maxpool_bwd_idx");
 }
 
 int cy4_f32_to_f16(const float *src, int64_t lds, float scale, const float *dscale, void *dst, int64_t ldd, int64_t M, int C,

@@ -472,8 +472,14 @@ class Plan:
                 src = outs[inf["srcs"][0]]
                 Hi, Wi = info[inf["srcs"][0]]["H"], info[inf["srcs"][0]]["W"]
                 cur = out_view(ind)
-                self.fwd_ops.append((L.cy4_maxpool_fwd, (src.ptr, src.ld, cur.ptr, cur.ld, B, Hi, Wi, src.C, k, stride, pad)))
-                self.pools.append((ind, cur, src, k, stride, pad, Hi, Wi))
+                Hp, Wp = (Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1
+                if self.infer or k * k > 255:
+                    amax = None
+                    self.fwd_ops.append((L.cy4_maxpool_fwd, (src.ptr, src.ld, cur.ptr, cur.ld, B, Hi, Wi, src.C, k, stride, pad)))
+                else:       # training plan: keep the argmax (one byte per output element) for the backward routing
+                    amax = torch.empty(B * Hp * Wp * src.C, device=self.device, dtype=torch.uint8)
+                    self.fwd_ops.append((L.cy4_maxpool_fwd_idx, (src.ptr, src.ld, cur.ptr, cur.ld, amax.data_ptr(), B, Hi, Wi, src.C, k, stride, pad)))
+                self.pools.append((ind, cur, src, k, stride, pad, Hi, Wi, amax))
             elif t == "upsample":
                 assert int(block["stride"]) == 2
                 src = outs[inf["srcs"][0]]
@@ -915,15 +921,19 @@ class Plan:
                 if b is not None:                        # unfused: the conv branch receives the same gradient
                     accumulate_into(b, out.gptr, out.ld, out.st.M)
             elif kind == "pool":
-                _, out, src, k, stride, pad, Hi, Wi = r
+                _, out, src, k, stride, pad, Hi, Wi, amax = r
                 if not out.grad_has():
                     continue
                 need = B * Hi * Wi * src.C
                 if self.pool_scratch is None or self.pool_scratch.numel() < need:
                     self.pool_scratch = torch.zeros(need, device=dev, dtype=torch.float32)
                 self.pool_scratch[:need].zero_()
-                self._call(L.cy4_maxpool_bwd, src.ptr, src.ld, out.gptr, out.ld, self.pool_scratch.data_ptr(), B, Hi, Wi, src.C,
-                           k, stride, pad, st)
+                if amax is not None:
+                    self._call(L.cy4_maxpool_bwd_idx, amax.data_ptr(), out.gptr, out.ld, self.pool_scratch.data_ptr(), B, Hi, Wi, src.C,
+                               k, stride, pad, st)
+                else:
+                    self._call(L.cy4_maxpool_bwd, src.ptr, src.ld, out.gptr, out.ld, self.pool_scratch.data_ptr(), B, Hi, Wi, src.C,
+                               k, stride, pad, st)
                 acc = src.grad_mode()
                 self._call(L.cy4_f32_to_f16, self.pool_scratch.data_ptr(), src.C, 1.0, None, src.gptr, src.ld, B * Hi * Wi, src.C, acc, st)
             elif kind == "up":

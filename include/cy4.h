@@ -158,6 +158,7 @@ typedef struct cy4_conv_desc {
  * "pdl" (0|1; environment CY4_PDL sets the initial value): programmatic dependent launch of the tensor-core and BN / activation
  *   kernels -- each calls griddepcontrol.launch_dependents first thing and griddepcontrol.wait before its first global access,
  *   so the next kernel's blocks are placed and set up (barriers, TMEM, descriptors) while the previous grid drains;
+ * "ew_fwd_blocks_per_sm" (1..32, default 3) / "ew_bwd_blocks_per_sm" (default 2): grid caps of the BN / activation passes;
  * "ew_carveout" (0|1, default 0; read at a kernel's first launch): 1 = the BN / activation passes prefer the maximum shared-memory
  *   carve-out (experiment: measured slower, kept for the record);
  * "slab_stats" (0|1, default 1): CY4_CONV_STATS sums are read off the staged fp16 output slab (the statistics of the STORED tensor,
@@ -275,6 +276,12 @@ CY4_API int cy4_maxpool_fwd(const void *in, int64_t ldi, void *out, int64_t ldo,
 /* gscratch [B,H,W,C] fp32 (caller-zeroed) += routed gradients; follow with cy4_f32_to_f16 */
 CY4_API int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C,
                             int k, int stride, int pad, void *stream);
+/* The same pair with the argmax kept: the forward also writes, per output element, the window offset dy*k+dx of its first maximum
+ * (uint8 [B,Ho,Wo,C], k*k <= 255); the backward routes the gradients from those indices instead of re-scanning the windows. */
+CY4_API int cy4_maxpool_fwd_idx(const void *in, int64_t ldi, void *out, int64_t ldo, void *argmax, int B, int H, int W, int C, int k,
+                                int stride, int pad, void *stream);
+CY4_API int cy4_maxpool_bwd_idx(const void *argmax, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C, int k,
+                                int stride, int pad, void *stream);
 /* dst (+)= fp16(scale * (dscale ? *dscale : 1) * src); dscale is a device scalar */
 CY4_API int cy4_f32_to_f16(const float *src, int64_t lds, float scale, const float *dscale, void *dst, int64_t ldd, int64_t M, int C,
                            int accumulate, void *stream);

@@ -366,9 +366,9 @@ def test_overlapped_wgrad_under_cuda_graph_replay():
         runs[mode] = losses
     print("losses one stream", runs[0], "overlapped", runs[2])
     # (two trainings from the same state drift apart through the atomically summed statistics, DESIGN.md section 5: the first
-    #  steps agree closely, later ones to the measured run-to-run spread)
+    #  step agrees closely, the ones after an optimizer update to the measured run-to-run spread)
     for i, (a, b) in enumerate(zip(runs[0], runs[2])):
-        assert abs(a - b) <= (2e-3 if i < 2 else 3e-2) * abs(a), (runs[0], runs[2])
+        assert abs(a - b) <= (1e-3 if i == 0 else 3e-2) * abs(a), (runs[0], runs[2])
 
 
 def test_programmatic_dependent_launch_gives_the_same_step():
@@ -399,7 +399,7 @@ def test_programmatic_dependent_launch_gives_the_same_step():
         print("losses plain", runs[(0, False)], "pdl eager", runs[(1, False)], "pdl graph", runs[(1, True)])
         for key in ((1, False), (1, True)):      # (same drift as any two runs: DESIGN.md section 5)
             for i, (a, b) in enumerate(zip(runs[(0, False)], runs[key])):
-                assert abs(a - b) <= (2e-3 if i < 2 else 3e-2) * abs(a), (key, runs)
+                assert abs(a - b) <= (1e-3 if i == 0 else 3e-2) * abs(a), (key, runs)
         # gradients on ONE forward state
         torch.manual_seed(1)
         model = Darknet(netdefs.cfg_path("complex_yolov4"), True).cuda().train()
@@ -496,6 +496,12 @@ def test_elementwise_kernels_vs_torch():
         _lib.check(L.cy4_maxpool_bwd(xin.data_ptr(), Cq, go.data_ptr(), Cq, scratch.data_ptr(), Bq, Hq, Wq, Cq, k, s, pad, st))
         ref.backward(go.float().permute(0, 3, 1, 2))
         assert (scratch - xf.grad.permute(0, 2, 3, 1)).abs().max().item() < 2e-2
+        # the argmax-keeping pair: same outputs, same routing (torch's first-maximum rule)
+        out2 = torch.empty_like(out); amax = torch.empty(Bq * Ho * Ho * Cq, device="cuda", dtype=torch.uint8)
+        _lib.check(L.cy4_maxpool_fwd_idx(xin.data_ptr(), Cq, out2.data_ptr(), Cq, amax.data_ptr(), Bq, Hq, Wq, Cq, k, s, pad, st))
+        scratch2 = torch.zeros_like(scratch)
+        _lib.check(L.cy4_maxpool_bwd_idx(amax.data_ptr(), go.data_ptr(), Cq, scratch2.data_ptr(), Bq, Hq, Wq, Cq, k, s, pad, st))
+        assert torch.equal(out2, out) and (scratch2 - scratch).abs().max().item() < 1e-3
     up = torch.empty(2, 38, 38, 64, device="cuda", dtype=torch.float16)
     _lib.check(L.cy4_upsample2x_fwd(x16.data_ptr(), 64, up.data_ptr(), 64, 2, 19, 19, 64, st))
     assert torch.equal(up, x16.repeat_interleave(2, 1).repeat_interleave(2, 2))

@@ -152,11 +152,14 @@ def fprop(path, out):
             v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1)
         k[r["Metric Name"]] = v
     rows = list(per.values())
+    if len(rows) > 110:
+        print("note: %d launches in the file, keeping the first 110 (the forward ones)" % len(rows))
+        rows = rows[:110]
     rd = sum(r.get("dram__bytes_read.sum", 0) for r in rows); wr = sum(r.get("dram__bytes_write.sum", 0) for r in rows)
     dur = sum(r.get("gpu__time_duration.sum", 0) for r in rows)
     tk = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
     tw = sum(r.get(tk, 0) * r.get("gpu__time_duration.sum", 0) for r in rows) / dur if dur else 0
-    txt = ["# ncu metric pass over the %d fprop launches of conv_tc_kernel in one bs=32 training step (%s)" % (len(rows), os.path.basename(path)),
+    txt = ["# ncu metric pass over the %d conv fprop launches (conv_pair_kernel / conv_tc_kernel) of one bs=32 training-mode forward (%s)" % (len(rows), os.path.basename(path)),
            "# serialised, cold-cache durations; DRAM bytes are what roofline.traffic reports (mean per launch)",
            "", "launches %d | sum dur %.3f ms | DRAM read %.3f GB | DRAM write %.3f GB | mean bytes/launch %.1f MB | algorithmic 14.4 GB/fwd (SURVEY 8d) -> ratio %.2f | tensor-pipe active (time-weighted) %.1f %%"
            % (len(rows), dur / 1e3, rd / 1e9, wr / 1e9, (rd + wr) / max(len(rows), 1) / 1e6, (rd + wr) / 14.4e9, tw),
@@ -166,7 +169,7 @@ def fprop(path, out):
                                                         r.get("dram__bytes_write.sum", 0) / 1e6, r.get(tk, 0)))
     open(out, "w").write("\n".join(txt) + "\n")
     print("\n".join(txt[:5]))
-    json.dump({"source": "%s (ncu metric pass of this round's shipped conv_tc_kernel, the %d fprop launches of one bs=32 step)" % (os.path.basename(out), len(rows)),
+    json.dump({"source": "%s (ncu metric pass of the shipped conv_pair_kernel / conv_tc_kernel, the %d fprop launches of one bs=32 step, tools/ncu_fprop_step.py)" % (os.path.basename(out), len(rows)),
                "dram_bytes_read": rd, "dram_bytes_write": wr, "launches": len(rows), "bytes_per_launch": (rd + wr) / max(len(rows), 1),
                "ncu_time_ms_cold": dur / 1e3, "tensor_pipe_active_pct_time_weighted": tw},
               open(os.path.join(os.path.dirname(out), "r2_conv_fprop_traffic.json"), "w"), indent=1)
