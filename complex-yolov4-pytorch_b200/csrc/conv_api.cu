@@ -31,6 +31,7 @@ int g_accum_tma = 1;        // accumulate-mode outputs through TMA reduce-add st
 int g_pdl = getenv("CY4_PDL") ? atoi(getenv("CY4_PDL")) : 0;   // programmatic dependent launch of the hot kernels (common.cuh)
 int g_ew_fwd_bpsm = 3, g_ew_bwd_bpsm = 2;   // grid caps of the BN / activation passes in blocks per SM (one resident wave each)
 int g_ew_carveout = 0;      // 1: BN / activation passes ask for the max shared-memory carve-out (measured: -0.7 ms/step WORSE, the passes want their L1)
+int g_dgrad_interleave = 1; // merged stride-2 dgrad: the four parity classes of a tile in neighbouring work units (dY re-reads hit L2)
 int g_slab_stats = 1;       // BatchNorm statistics read off the staged fp16 output slab (0: reduce-scatter over the fp32 accumulators)
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
@@ -74,6 +75,8 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     p.epi_mode = g.epi_mode; p.epi_act = g.epi_act; p.epi_scale = g.epi_scale; p.epi_shift = g.epi_shift;
     p.side = g.side; p.ld_side = g.ld_side;
     p.ncls = g.ncls;
+    // (small layers: dY stays in the 126 MB L2 between the class passes, and their few units per CTA balance better class-major)
+    p.cls_interleave = g_dgrad_interleave && g.ncls > 1 && (int64_t)g.B * g.Ha * g.Wa * g.Ca * 2 >= (64ll << 20);
     int min_taps = g.ntaps;
     for (int c = 0; c < g.ncls && c < 4; ++c) {
         p.cls_tap0[c] = g.cls_tap0[c]; p.cls_ntap[c] = g.cls_ntap[c]; p.cls_oh0[c] = g.cls_oh0[c]; p.cls_ow0[c] = g.cls_ow0[c];
@@ -368,6 +371,7 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "ew_fwd_blocks_per_sm")) { CY4_CHECK_ARG(value >= 1 && value <= 32, "ew_fwd_blocks_per_sm must be in 1..32"); g_ew_fwd_bpsm = value; return 0; }
     if (!strcmp(name, "ew_bwd_blocks_per_sm")) { CY4_CHECK_ARG(value >= 1 && value <= 32, "ew_bwd_blocks_per_sm must be in 1..32"); g_ew_bwd_bpsm = value; return 0; }
     if (!strcmp(name, "ew_carveout")) { g_ew_carveout = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "dgrad_interleave")) { g_dgrad_interleave = value ? 1 : 0; return 0; }
     if (!strcmp(name, "slab_stats")) { g_slab_stats = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv_pair")) { g_conv_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage

@@ -93,7 +93,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int t = unit0; t < units; t += unit_step) {
-                const int cls = t / cls_units, tt = t - cls * cls_units;
+                int cls, tt;
+                unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt);
                 const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
                 const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * 2 + crank;
                 const int m0 = m_blk * kPM;
@@ -129,7 +130,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);         // both CTAs' epilogues have drained this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.block_n;
-                const int num_kb = (ncls > 1 ? p.cls_ntap[t / cls_units] : p.ntaps) * p.cin_chunks;
+                int cls, tt_;
+            unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt_);
+            const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&ctl->full[stage], phase);
                     tc_fence_after();
@@ -157,7 +160,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int slab_i = 0;
         for (int t = unit0; t < units; t += unit_step, ++seq) {
             if ((seq & 1) != group) continue;
-            const int cls = t / cls_units, tt = t - cls * cls_units;
+            int cls, tt;
+                unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt);
             const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * 2 + crank;
             const int m = m_blk * kPM + quarter * 32 + lane;
             const bool row_ok = m < p.M;

@@ -135,7 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
             for (int t = unit0; t < units; t += unit_step) {
-                const int cls = t / cls_units, tt = t - cls * cls_units;
+                int cls, tt;
+                unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt);
                 const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
                 const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * cs + crank;
                 const int m0 = m_blk * kBlockM;
@@ -189,7 +190,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             PROBE_ACC(0);
             const uint32_t d_tmem = tmem_base + acc * p.block_n;
-            const int num_kb = (ncls > 1 ? p.cls_ntap[t / cls_units] : p.ntaps) * p.cin_chunks;
+            int cls, tt_;
+            unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt_);
+            const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
             for (int g0 = 0; g0 < num_kb; g0 += kps) {
                 const int cnt = min(kps, num_kb - g0);
                 PROBE_T0;
@@ -235,7 +238,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int slab_i = 0;                               // rotating output slab of this warp
         for (int t = unit0; t < units; t += unit_step, ++seq) {
             if ((seq & 1) != group) continue;
-            const int cls = t / cls_units, tt = t - cls * cls_units;
+            int cls, tt;
+                unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt);
             const int n_blk = tt % p.tiles_n, m_blk = (tt / p.tiles_n) * cs + crank;
             const int m = m_blk * kBlockM + quarter * 32 + lane;          // this thread's GEMM row
             const bool row_ok = m < p.M;

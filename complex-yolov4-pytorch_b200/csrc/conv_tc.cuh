@@ -55,12 +55,28 @@ struct ConvKParams {
     // offsets, all over the same Po x Qo base-pixel grid).  Work unit t -> class t / cls_units.  ncls <= 1: one class made of
     // taps [0, ntaps) and (oh0, ow0) above.
     int ncls, cls_units;
+    int cls_interleave;          // 1: unit -> (tile t / ncls, class rotated per tile), see unit_decode
     uint8_t cls_tap0[4], cls_ntap[4], cls_oh0[4], cls_ow0[4];
     // fused epilogue
     int epi_mode, epi_act;
     const float *epi_scale, *epi_shift;  // per output channel
     const void *side; int64_t ld_side;   // fp16 [rows, ld_side], same row mapping as y
 };
+
+// Work unit t of a launch with several tap classes -> (class, tile of that class).  Class-major order (t / cls_units) walks the
+// whole dY tensor once PER CLASS: 4 DRAM passes over dY for the stride-2 input gradients (ncu: 1.1 GB of DRAM traffic for 0.57 GB
+// of algorithmic bytes on the 64->128 layer).  Interleaved order puts the four classes of one tile into units 4*tile .. 4*tile+3,
+// which neighbouring CTAs process at the same time, so three of the four dY reads hit L2.  The class of a unit is rotated by the
+// tile index: a function of the tile only (each tile still gets every class exactly once) that makes every CTA of the static
+// round-robin cycle through all classes (they carry 1 / 2 / 2 / 4 taps) for grids of 148 CTAs and of 74 CTA pairs alike (max / mean
+// load 1.01-1.03 on the layers it is used for; the host enables it only when dY exceeds what L2 keeps, conv_api.cu).
+__device__ __forceinline__ void unit_decode(int t, int cls_units, int ncls, int interleave, int grid_units, int &cls, int &tt)
+{
+    if (ncls <= 1) { cls = 0; tt = t; return; }
+    if (!interleave) { cls = t / cls_units; tt = t - cls * cls_units; return; }
+    tt = t / ncls;
+    cls = (t - tt * ncls + tt) % ncls;
+}
 
 int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer, int swizzle_bytes, int dtype_bf16);

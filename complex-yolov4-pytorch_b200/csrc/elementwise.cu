@@ -430,9 +430,83 @@ maxpool_fwd_kernel(const __half *__restrict__ in, int64_t ldi, __half *__restric
         *(uint4 *)(out + (((int64_t)b * Ho + oh) * Wo + ow) * ldo + c0) = pack8(best);
     }
 }
-// Forward that also records, per output element, WHICH window element was the first maximum (torch's scan order) as the
-// window offset dy * k + dx in one byte: the backward pass then routes gradients without re-scanning the k x k windows
+// Forward that also records, per output element, WHICH window element was the first maximum (torch's row-major scan order) as
+// the window offset dy * k + dx in one byte: the backward pass then routes gradients without re-scanning the k x k windows
 // (169 16-byte loads per output vector for the 13 x 13 SPP pool).
+// Separable, stride 1: a vertical pass (column maximum + the smallest dy that attains it) into a workspace, then a horizontal
+// pass over the column maxima with the tie-break (smaller dy, then smaller dx) -- which IS the first maximum of the row-major scan:
+// the minimal dy over all maxima is the minimum of the columns' dy, and among those columns the leftmost wins.  2k loads per
+// output instead of k^2.  Rows / columns outside the image are skipped (padding never wins).
+__global__ void __launch_bounds__(256)
+maxpool_v_kernel(const __half *__restrict__ in, int64_t ldi, __half *__restrict__ vmax, uint8_t *__restrict__ vdy, int B, int H, int W, int C,
+                 int k, int pad)
+{
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * H * W * vpr;              // one entry per (output row oh, input column w): Ho == H for stride 1
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
+        const int w = (int)(r % W); r /= W;
+        const int oh = (int)(r % H);
+        const int b = (int)(r / H);
+        float best[8], t[8]; int bdy[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bdy[q] = -1; }
+        for (int dy = 0; dy < k; ++dy) {
+            const int h = oh - pad + dy;
+            if (h < 0 || h >= H) continue;
+            unpack8(*(const uint4 *)(in + (((int64_t)b * H + h) * W + w) * ldi + c0), t);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (t[q] > best[q] || bdy[q] < 0) { best[q] = t[q]; bdy[q] = dy; }
+        }
+        const int64_t o = ((int64_t)b * H + oh) * W + w;
+        *(uint4 *)(vmax + o * C + c0) = pack8(best);
+        uint2 pk;
+        pk.x = (uint32_t)bdy[0] | ((uint32_t)bdy[1] << 8) | ((uint32_t)bdy[2] << 16) | ((uint32_t)bdy[3] << 24);
+        pk.y = (uint32_t)bdy[4] | ((uint32_t)bdy[5] << 8) | ((uint32_t)bdy[6] << 16) | ((uint32_t)bdy[7] << 24);
+        *(uint2 *)(vdy + o * C + c0) = pk;
+    }
+}
+__global__ void __launch_bounds__(256)
+maxpool_h_kernel(const __half *__restrict__ vmax, const uint8_t *__restrict__ vdy, __half *__restrict__ out, int64_t ldo,
+                 uint8_t *__restrict__ argmax, int B, int H, int W, int C, int k, int pad)
+{
+    const int vpr = C >> 3;
+    const int64_t total = (int64_t)B * H * W * vpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / vpr;
+        const int c0 = (int)(i - r * vpr) << 3;
+        const int ow = (int)(r % W); r /= W;
+        const int oh = (int)(r % H);
+        const int b = (int)(r / H);
+        float best[8], t[8]; int bdy[8], bdx[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bdy[q] = 1 << 20; bdx[q] = -1; }
+        for (int dx = 0; dx < k; ++dx) {
+            const int w = ow - pad + dx;
+            if (w < 0 || w >= W) continue;
+            const int64_t o = ((int64_t)b * H + oh) * W + w;
+            unpack8(*(const uint4 *)(vmax + o * C + c0), t);
+            const uint2 pk = *(const uint2 *)(vdy + o * C + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int dy = (int)(((q < 4 ? pk.x : pk.y) >> ((q & 3) * 8)) & 255u);
+                if (bdx[q] < 0 || t[q] > best[q] || (t[q] == best[q] && dy < bdy[q])) { best[q] = t[q]; bdy[q] = dy; bdx[q] = dx; }
+            }
+        }
+        const int64_t o = ((int64_t)b * H + oh) * W + ow;
+        *(uint4 *)(out + o * ldo + c0) = pack8(best);
+        int pos[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pos[q] = bdy[q] * k + bdx[q];
+        uint2 pk;
+        pk.x = (uint32_t)pos[0] | ((uint32_t)pos[1] << 8) | ((uint32_t)pos[2] << 16) | ((uint32_t)pos[3] << 24);
+        pk.y = (uint32_t)pos[4] | ((uint32_t)pos[5] << 8) | ((uint32_t)pos[6] << 16) | ((uint32_t)pos[7] << 24);
+        *(uint2 *)(argmax + o * C + c0) = pk;
+    }
+}
+// general (strided) form: one k x k scan per output
 __global__ void __launch_bounds__(256)
 maxpool_fwd_idx_kernel(const __half *__restrict__ in, int64_t ldi, __half *__restrict__ out, int64_t ldo, uint8_t *__restrict__ argmax,
                        int B, int H, int W, int C, int k, int s, int pad, int Ho, int Wo)
@@ -813,12 +887,21 @@ int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, 
     return cy4_launch_status("cy4_maxpool_bwd");
 }
 
-int cy4_maxpool_fwd_idx(const void *in, int64_t ldi, void *out, int64_t ldo, void *argmax, int B, int H, int W, int C, int k, int stride,
-                        int pad, void *stream)
+int cy4_maxpool_fwd_idx(const void *in, int64_t ldi, void *out, int64_t ldo, void *argmax, void *workspace, int B, int H, int W, int C, int k,
+                        int stride, int pad, void *stream)
 {
     EW_CHECK_C(C, "cy4_maxpool_fwd_idx");
     CY4_CHECK_ARG(in && out && argmax && k > 0 && k * k <= 255 && stride > 0, "cy4_maxpool_fwd_idx: bad argument (window of at most 255 elements)");
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    const int64_t n = (int64_t)B * H * W * C;
+    if (workspace && stride == 1 && Ho == H && Wo == W) {
+        // separable: column maxima (+ first dy) into the workspace [n halves | n bytes], then the row pass
+        __half *vmax = (__half *)workspace;
+        uint8_t *vdy = (uint8_t *)workspace + 2 * n;
+        maxpool_v_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, vmax, vdy, B, H, W, C, k, pad);
+        maxpool_h_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(vmax, vdy, (__half *)out, ldo, (uint8_t *)argmax, B, H, W, C, k, pad);
+        return cy4_launch_status("cy4_maxpool_fwd_idx", 2);
+    }
     maxpool_fwd_idx_kernel<<<ew_grid((int64_t)B * Ho * Wo * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)in, ldi, (__half *)out, ldo,
                                                                                                 (uint8_t *)argmax, B, H, W, C, k, stride, pad, Ho, Wo);
     return cy4_launch_status("cy4_maxpool_fwd_idx");

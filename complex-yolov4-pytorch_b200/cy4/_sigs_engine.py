@@ -58,7 +58,7 @@ SIGS = {
     "cy4_upsample2x_bwd": (c_i, [c_f, c_i64, c_f, c_i64, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "cy4_maxpool_fwd": (c_i, [c_f, c_i64, c_f, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "cy4_maxpool_bwd": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
-    "cy4_maxpool_fwd_idx": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
+    "cy4_maxpool_fwd_idx": (c_i, [c_f, c_i64, c_f, c_i64, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "cy4_maxpool_bwd_idx": (c_i, [c_f, c_f, c_i64, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
     "cy4_f32_to_f16": (c_i, [c_f, c_i64, ctypes.c_float, c_f, c_f, c_i64, c_i64, c_i, c_i, c_vp]),
     "cy4_colsum_f32": (c_i, [c_f, c_i64, c_i64, c_i, ctypes.c_float, c_f, c_i, c_vp]),

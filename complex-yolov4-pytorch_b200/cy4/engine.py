@@ -478,7 +478,10 @@ class Plan:
                     self.fwd_ops.append((L.cy4_maxpool_fwd, (src.ptr, src.ld, cur.ptr, cur.ld, B, Hi, Wi, src.C, k, stride, pad)))
                 else:       # training plan: keep the argmax (one byte per output element) for the backward routing
                     amax = torch.empty(B * Hp * Wp * src.C, device=self.device, dtype=torch.uint8)
-                    self.fwd_ops.append((L.cy4_maxpool_fwd_idx, (src.ptr, src.ld, cur.ptr, cur.ld, amax.data_ptr(), B, Hi, Wi, src.C, k, stride, pad)))
+                    if getattr(self, "pool_ws", None) is None or self.pool_ws.numel() < 3 * B * Hi * Wi * src.C:
+                        self.pool_ws = torch.empty(3 * B * Hi * Wi * src.C, device=self.device, dtype=torch.uint8)   # separable-pass workspace
+                    self.fwd_ops.append((L.cy4_maxpool_fwd_idx, (src.ptr, src.ld, cur.ptr, cur.ld, amax.data_ptr(), self.pool_ws.data_ptr(),
+                                                                 B, Hi, Wi, src.C, k, stride, pad)))
                 self.pools.append((ind, cur, src, k, stride, pad, Hi, Wi, amax))
             elif t == "upsample":
                 assert int(block["stride"]) == 2

@@ -161,6 +161,8 @@ typedef struct cy4_conv_desc {
  * "ew_fwd_blocks_per_sm" (1..32, default 3) / "ew_bwd_blocks_per_sm" (default 2): grid caps of the BN / activation passes;
  * "ew_carveout" (0|1, default 0; read at a kernel's first launch): 1 = the BN / activation passes prefer the maximum shared-memory
  *   carve-out (experiment: measured slower, kept for the record);
+ * "dgrad_interleave" (0|1, default 1): merged stride-2 input gradients whose dY exceeds 64 MB walk the four output-parity classes
+ *   of a tile in neighbouring work units (three of the four dY reads hit L2) instead of class after class (four DRAM passes);
  * "slab_stats" (0|1, default 1): CY4_CONV_STATS sums are read off the staged fp16 output slab (the statistics of the STORED tensor,
  *   ~100 instructions per 32x32 slab) instead of a shuffle reduce-scatter over the fp32 accumulators (~400, a dependent chain);
  * "debug": bottleneck experiments, honoured only by -DCY4_PROBE side builds (tools/probe_pipeline.py). */
@@ -277,9 +279,10 @@ CY4_API int cy4_maxpool_fwd(const void *in, int64_t ldi, void *out, int64_t ldo,
 CY4_API int cy4_maxpool_bwd(const void *in, int64_t ldi, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C,
                             int k, int stride, int pad, void *stream);
 /* The same pair with the argmax kept: the forward also writes, per output element, the window offset dy*k+dx of its first maximum
- * (uint8 [B,Ho,Wo,C], k*k <= 255); the backward routes the gradients from those indices instead of re-scanning the windows. */
-CY4_API int cy4_maxpool_fwd_idx(const void *in, int64_t ldi, void *out, int64_t ldo, void *argmax, int B, int H, int W, int C, int k,
-                                int stride, int pad, void *stream);
+ * (uint8 [B,Ho,Wo,C], k*k <= 255); the backward routes the gradients from those indices instead of re-scanning the windows.
+ * workspace: NULL, or 3*B*H*W*C bytes (16-byte aligned): stride-1 "same" pools then run as two separable passes (2k loads per output). */
+CY4_API int cy4_maxpool_fwd_idx(const void *in, int64_t ldi, void *out, int64_t ldo, void *argmax, void *workspace, int B, int H, int W,
+                                int C, int k, int stride, int pad, void *stream);
 CY4_API int cy4_maxpool_bwd_idx(const void *argmax, const void *gout, int64_t ldo, float *gscratch, int B, int H, int W, int C, int k,
                                 int stride, int pad, void *stream);
 /* dst (+)= fp16(scale * (dscale ? *dscale : 1) * src); dscale is a device scalar */

@@ -481,8 +481,9 @@ def test_elementwise_kernels_vs_torch():
         assert (dy.float() - gref).abs().max().item() < 5e-3 * gref.abs().max().item() + 1e-3
     # max pool (SPP sizes + 2x2/2) and its gradient routing, upsample
     x16 = torch.randn(2, 19, 19, 64, device="cuda").half()
-    for k, s in ((5, 1), (9, 1), (13, 1), (2, 2)):
-        xin = x16[:, :18, :18].contiguous() if s == 2 else x16
+    xq = (torch.randn(2, 19, 19, 64, device="cuda") * 2).round().div(2).half()      # coarse values: many tied maxima per window
+    for k, s, xsrc in ((5, 1, x16), (9, 1, x16), (13, 1, x16), (2, 2, x16), (5, 1, xq), (13, 1, xq), (2, 2, xq)):
+        xin = xsrc[:, :18, :18].contiguous() if s == 2 else xsrc
         Bq, Hq, Wq, Cq = xin.shape
         pad = k // 2 if s == 1 else 0
         Ho = (Hq + 2 * pad - k) // s + 1
@@ -498,10 +499,13 @@ def test_elementwise_kernels_vs_torch():
         assert (scratch - xf.grad.permute(0, 2, 3, 1)).abs().max().item() < 2e-2
         # the argmax-keeping pair: same outputs, same routing (torch's first-maximum rule)
         out2 = torch.empty_like(out); amax = torch.empty(Bq * Ho * Ho * Cq, device="cuda", dtype=torch.uint8)
-        _lib.check(L.cy4_maxpool_fwd_idx(xin.data_ptr(), Cq, out2.data_ptr(), Cq, amax.data_ptr(), Bq, Hq, Wq, Cq, k, s, pad, st))
-        scratch2 = torch.zeros_like(scratch)
-        _lib.check(L.cy4_maxpool_bwd_idx(amax.data_ptr(), go.data_ptr(), Cq, scratch2.data_ptr(), Bq, Hq, Wq, Cq, k, s, pad, st))
-        assert torch.equal(out2, out) and (scratch2 - scratch).abs().max().item() < 1e-3
+        ws = torch.empty(3 * Bq * Hq * Wq * Cq, device="cuda", dtype=torch.uint8)
+        for wsp in (None, ws.data_ptr()):          # one k x k scan per output / the two separable passes (stride 1)
+            out2.zero_(); amax.zero_()
+            _lib.check(L.cy4_maxpool_fwd_idx(xin.data_ptr(), Cq, out2.data_ptr(), Cq, amax.data_ptr(), wsp, Bq, Hq, Wq, Cq, k, s, pad, st))
+            scratch2 = torch.zeros_like(scratch)
+            _lib.check(L.cy4_maxpool_bwd_idx(amax.data_ptr(), go.data_ptr(), Cq, scratch2.data_ptr(), Bq, Hq, Wq, Cq, k, s, pad, st))
+            assert torch.equal(out2, out) and (scratch2 - scratch).abs().max().item() < 1e-3
     up = torch.empty(2, 38, 38, 64, device="cuda", dtype=torch.float16)
     _lib.check(L.cy4_upsample2x_fwd(x16.data_ptr(), 64, up.data_ptr(), 64, 2, 19, 19, 64, st))
     assert torch.equal(up, x16.repeat_interleave(2, 1).repeat_interleave(2, 2))
