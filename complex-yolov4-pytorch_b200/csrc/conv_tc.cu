@@ -255,10 +255,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&ctl->tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * p.block_n;
-            for (int c = 0; c < p.block_n / 32; ++c) {
+            const int nchunks = p.block_n / 32;
+            for (int c = 0; c < nchunks; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c * 32, v);
                 tmem_ld_wait();
+                if (c == nchunks - 1 && !(p.flags & CONV_F_LATE_RELEASE)) {
+                    // The accumulator stage is free as soon as its LAST columns are in registers: hand it back to the MMA warp
+                    // here, not after the store / statistics work below.  Narrow, short-K tiles (N = 32..64, K = 32..128) are
+                    // bound by exactly this round trip: two accumulator stages per epilogue latency.
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+                }
                 const int n0 = n_blk * p.block_n + c * 32;
                 float f[32];
 #pragma unroll
@@ -274,11 +283,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // (32 columns = 64-byte rows, 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3)
                     // Narrow layers are bound by the TMA-store round trip of this slab, so they rotate through
                     // up to 4 slabs per warp (extra slabs live at the tail of the 192 KB stage region).
-                    uint8_t *slab = (slab_i == 0 ? sOut : smem + kStages * (kAStageBytes + kBStageBytes) - slab_i * kOutStageBytes) + (warp - 2) * (32 * 64);
+                    // Group store (CONV_F_GROUP_STORE, narrow tiles): the TMA unit handles a bulk-tensor INSTRUCTION every few hundred
+                    // cycles whatever its size, and a 128 x 32 tile with one or two k-blocks issues 2-4 loads but 4 stores of 2 KB.
+                    // The four warps of an epilogue group lay their slabs out in row order (8 KB), meet at a named barrier, and ONE
+                    // thread stores the 128 rows.  Slab reuse: slab (c mod S) was last read by the store of chunk c - S; the issuer
+                    // waits for it (at most S - 2 younger stores pending) before it arrives at the barrier of chunk c - 1, which
+                    // every warp passes before it writes chunk c.
+                    const bool gstore = (p.flags & CONV_F_GROUP_STORE) != 0;
+                    uint8_t *blk = slab_i == 0 ? sOut : smem + kStages * (kAStageBytes + kBStageBytes) - slab_i * kOutStageBytes;
+                    uint8_t *gslab = blk + group * (4 * 32 * 64);
+                    uint8_t *slab = gstore ? gslab + quarter * (32 * 64) : blk + (warp - 2) * (32 * 64);
                     const int cw = 32;
                     const int sub = 0;
-                    if (lane == 0) tma_store_wait_read_n(p.slab_bufs - 1);   // the store that used this slab has read it
-                    __syncwarp();
+                    if (!gstore) {
+                        if (lane == 0) tma_store_wait_read_n(p.slab_bufs - 1);   // the store that used this slab has read it
+                        __syncwarp();
+                    }
                     if (++slab_i == p.slab_bufs) slab_i = 0;
                     const int rowbytes = cw * 2;
                     const int xr = (lane >> 1) & 3;
@@ -290,8 +310,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int chunk = (sub + i) >> 3;            // 16-byte chunk index inside the row
                         *(uint4 *)(slab + lane * rowbytes + ((chunk ^ xr) << 4)) = o;
                     }
-                    if (sub + 32 == cw) {                            // slab complete
-                        fence_proxy_async();
+                    fence_proxy_async();
+                    if (gstore) {
+                        named_bar_sync(1 + group, 128);
+                        if (quarter == 0 && lane == 0) {
+                            if (p.flags & CONV_F_ACCUM) tma_reduce_add_2d(&tmC, gslab, n_blk * p.block_n + c * 32, m_blk * kBlockM);
+                            else tma_store_2d(&tmC, gslab, n_blk * p.block_n + c * 32, m_blk * kBlockM);
+                            tma_store_commit();
+                            tma_store_wait_read_n(p.slab_bufs - 2);
+                        }
+                    } else {
                         __syncwarp();
                         if (lane == 0) {
                             if (p.flags & CONV_F_ACCUM) tma_reduce_add_2d(&tmC, slab, n_blk * p.block_n + c * 32 - sub, m_blk * kBlockM + quarter * 32);
@@ -392,9 +420,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+            if (p.flags & CONV_F_LATE_RELEASE) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+            }
             acc_phase ^= 1;
         }
     }

@@ -11,6 +11,8 @@ enum : uint32_t {
     CONV_F_STATS = 2u,     // accumulate per-channel sum / sum^2 of the fp32 accumulators
     CONV_F_ACCUM = 4u,     // y += result (fp16 read-modify-write), used by dgrad into shared grads
     CONV_F_TMA_OUT = 16u,  // internal: fp16 tile staged in swizzled smem and written with TMA stores
+    CONV_F_GROUP_STORE = 128u, // internal: ONE TMA store of 128 rows per tile chunk (issued for the 4 epilogue warps of a group) instead of four of 32 rows
+    CONV_F_LATE_RELEASE = 64u, // internal (option early_acc_release=0): hand the TMEM accumulator back after the whole epilogue of the tile
     CONV_F_ACC_STATS = 32u,// internal (option slab_stats=0): statistics by reduce-scatter over the fp32 accumulators even when a slab is staged
 };
 
