@@ -41,7 +41,7 @@ constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + kCtlBytes + 2 * kMaxSta
 constexpr uint32_t kTmemCols = 512;
 
 struct SmemCtl {
-    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
+    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], bres_full;
     uint32_t tmem_base;
 };
 
@@ -88,8 +88,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The TMA -> MMA round trip is ~1.5-2 us; a slot only holds 12..48 KB, so narrow / small-K layers need
     // many more slots in flight than the 4 that fit for the 128x256x64 tile (measured).
     const int nst = p.stages, kps = p.kps;
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + nst * kps * p.a_stage;
+    // Resident weights (p.bres_bytes > 0: narrow layers with one n tile whose whole packed weight matrix is <= 80 KB): every k-block
+    // of B is loaded ONCE per CTA into the head of the stage region and the pipeline slots carry activations only -- the producer
+    // thread issues one bulk-tensor load per k-block instead of two (these layers are bound by its issue loop).
+    const bool bres = p.bres_bytes > 0;
+    uint8_t *sA = smem + p.bres_bytes;
+    uint8_t *sB = bres ? smem : sA + nst * kps * p.a_stage;
     uint8_t *sOut = smem + kStages * (kAStageBytes + kBStageBytes);
     SmemCtl *ctl = (SmemCtl *)(smem + kCtlOffset);
     float *sstat = (float *)(smem + kCtlOffset + kCtlBytes);     // [2][kMaxStatCh]
@@ -118,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.flags & CONV_F_TMA_OUT) prefetch_tmap(&tmC);
         for (int s = 0; s < nst; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
+        mbar_init(&ctl->bres_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(&ctl->tmem_base);
@@ -134,6 +139,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             PPROBE_DECL;
             int stage = 0; uint32_t phase = 0;
             const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
+            if (bres) {                                        // the whole weight matrix, once: k-block (tap, cc) at index tap * cin_chunks + cc
+                mbar_expect_tx(&ctl->bres_full, (uint32_t)(p.ntaps * p.cin_chunks) * b_bytes);
+                for (int tp = 0; tp < p.ntaps; ++tp)
+                    for (int c2 = 0; c2 < p.cin_chunks; ++c2)
+                        tma_load_2d(&tmB, &ctl->bres_full, sB + (tp * p.cin_chunks + c2) * p.b_stage, p.tap_kofs[tp] + c2 * p.kchunk, 0);
+            }
             for (int t = unit0; t < units; t += unit_step) {
                 int cls, tt;
                 unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt);
@@ -152,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     PPROBE_ACC(0);
                     if (CY4_DBG == 2 || CY4_DBG == 3 || CY4_DBG == 6) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == nst) { stage = 0; phase ^= 1; } continue; }
-                    mbar_expect_tx(&ctl->full[stage], (uint32_t)cnt * (a_bytes + b_bytes));
+                    mbar_expect_tx(&ctl->full[stage], (uint32_t)cnt * (a_bytes + (bres ? 0u : b_bytes)));
                     for (int j = 0; j < cnt; ++j) {
                         const int slot = stage * kps + j;
                         if (p.a_mode == 1)
@@ -160,7 +171,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
                         else
                             tma_load_2d(&tmA, &ctl->full[stage], sA + slot * p.a_stage, cc * p.kchunk, m0);
-                        if (cs > 1)
+                        if (bres) {
+                        } else if (cs > 1)
                             tma_load_2d_mc(&tmB, &ctl->full[stage], sB + slot * p.b_stage + crank * b_rows * p.kchunk * 2,
                                            p.tap_kofs[tap] + cc * p.kchunk, n_blk * p.block_n + crank * b_rows, cmask);
                         else
@@ -183,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_step = (uint32_t)p.a_stage >> 4, b_step = (uint32_t)p.b_stage >> 4;
         const bool k64 = p.kchunk == 64;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        if (bres) { mbar_wait(&ctl->bres_full, 0); tc_fence_after(); }       // the resident weights have landed
         PROBE_DECL;
         for (int t = unit0; t < units; t += unit_step) {
             PROBE_T0;
@@ -193,6 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int cls, tt_;
             unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt_);
             const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
+            const int kb0 = (ncls > 1 ? p.cls_tap0[cls] : 0) * p.cin_chunks;    // first k-block of this tile's tap class
             for (int g0 = 0; g0 < num_kb; g0 += kps) {
                 const int cnt = min(kps, num_kb - g0);
                 PROBE_T0;
@@ -203,7 +217,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (elect_one()) {
                     // descriptor low words advance by whole slots (addresses are 1024-aligned and < 256 KB, so the
                     // 14-bit address field never carries): one multiply-add per operand per k-block
-                    uint32_t a_lo = a_lo0 + (uint32_t)(stage * kps) * a_step, b_lo = b_lo0 + (uint32_t)(stage * kps) * b_step;
+                    uint32_t a_lo = a_lo0 + (uint32_t)(stage * kps) * a_step;
+                    uint32_t b_lo = b_lo0 + (uint32_t)(bres ? kb0 + g0 : stage * kps) * b_step;     // resident: k-block index of the launch
                     for (int j = 0; j < cnt; ++j, a_lo += a_step, b_lo += b_step) {
                         if (CY4_DBG != 1 && CY4_DBG != 3 && CY4_DBG != 6) {
                             umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, (g0 + j) != 0);

@@ -41,6 +41,7 @@ struct ConvKParams {
     int debug;                   // 1: skip MMAs, 2: skip TMA loads (bottleneck experiments)
     int stages, a_stage, b_stage;   // pipeline depth and per-stage bytes (the 192 KB stage region is split to fit)
     int kps;                     // k-blocks per pipeline slot (one barrier round trip per kps k-blocks)
+    int bres_bytes;              // > 0: ALL weight k-blocks of the launch stay resident in the first bres_bytes of the stage region (1-CTA kernel, one n tile)
     int slab_bufs;               // output slabs per epilogue warp (1, 2 or 4): TMA-store latency hiding for narrow layers
     int ab_fmt;                  // 0 fp16, 1 bf16
     // im2col base-pixel space: pixel m -> (img, pi, qi) over Po x Qo ; TMA base = (qi*tstride + lower_w, ...)
