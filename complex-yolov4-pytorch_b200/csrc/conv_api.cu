@@ -32,9 +32,6 @@ int g_pdl = getenv("CY4_PDL") ? atoi(getenv("CY4_PDL")) : 0;   // programmatic d
 int g_ew_fwd_bpsm = 3, g_ew_bwd_bpsm = 2;   // grid caps of the BN / activation passes in blocks per SM (one resident wave each)
 int g_ew_carveout = 0;      // 1: BN / activation passes ask for the max shared-memory carve-out (measured: -0.7 ms/step WORSE, the passes want their L1)
 int g_dgrad_interleave = 1; // merged stride-2 dgrad: the four parity classes of a tile in neighbouring work units (dY re-reads hit L2)
-int g_early_release = 1;    // epilogue hands the TMEM accumulator stage back right after its last tcgen05.ld (0: after the whole tile epilogue)
-int g_group_store = 1;      // narrow 1-CTA tiles: one 128-row TMA store per tile chunk instead of one per epilogue warp
-int g_b_resident = 1;       // narrow 1-CTA launches keep their whole weight matrix resident in shared memory (conv_tc.cu)
 int g_slab_stats = 1;       // BatchNorm statistics read off the staged fp16 output slab (0: reduce-scatter over the fp32 accumulators)
 int g_conv1x1_matrix = 0;   // 1: 1x1 / stride-1 convs (fprop and dgrad) read their activation through a plain 2-D tiled TMA instead of im2col mode
 
@@ -114,19 +111,6 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     const int num_kb = min_taps * p.cin_chunks;          // (of the shortest tap class)
     p.kps = (p.cluster == 1 && g_kps_max > 1) ? std::max(1, std::min(std::min(g_kps_max, num_kb), 49152 / (p.a_stage + p.b_stage))) : 1;
     p.stages = std::max(2, std::min(12, (4 * 49152 - slab_extra) / (p.kps * (p.a_stage + p.b_stage))));
-    // Narrow layers (one n tile, 1-CTA kernel): keep the whole packed weight matrix resident in shared memory when it is at most
-    // 80 KB -- the slots then carry activations only and the producer thread issues half as many bulk-tensor loads.
-    p.bres_bytes = 0;
-    {
-        const int64_t all_b = (int64_t)g.ntaps * p.cin_chunks * p.b_stage;
-        const int64_t avail = 4 * 49152 - slab_extra - all_b;              // what is left of the stage region for activation slots
-        if (g_b_resident && !pair && p.cluster == 1 && p.tiles_n == 1 && all_b <= 80 * 1024 && avail >= 4 * p.a_stage) {
-            p.bres_bytes = (int)all_b;
-            const int fit = (int)(avail / (2 * p.a_stage));                 // k-blocks per slot such that two slots still fit
-            p.kps = g_kps_max > 1 ? std::max(1, std::min(std::min(std::min(g_kps_max, num_kb), 49152 / p.a_stage), fit)) : 1;
-            p.stages = std::max(2, std::min(12, (int)(avail / (p.kps * p.a_stage))));
-        }
-    }
     alignas(64) CUtensorMap tmC = tmB;
     // Accumulating launches (y += result: gradients of tensors with several consumers) keep the slab path too: the slab is
     // ADDED to global memory by a TMA reduce (cp.reduce.async.bulk.tensor ... .add, fp16) instead of a per-thread strided
@@ -135,15 +119,11 @@ static int run_generic(const GenericConv &g, cudaStream_t st)
     if (!(p.flags & CONV_F_OUT_F32) && (!(p.flags & CONV_F_ACCUM) || accum_tma) && !p.omap && !g_disable_tma_out) {
         // dense fp16 output: epilogue stages 32-row slabs in swizzled smem and TMA-stores them
         const int cw = 32;
-        // narrow tiles of the 1-CTA kernel (4 rotating slabs): one 128-row TMA store per tile chunk for the whole epilogue group
-        const bool gstore = g_group_store && !pair && p.slab_bufs >= 3;
-        if (gstore) p.flags |= CONV_F_GROUP_STORE;
-        rc = make_tmap_2d(&tmC, g.y, (uint64_t)g.w_rows_pad, (uint64_t)p.M, (uint64_t)g.ldy * 2, cw, gstore ? 128 : 32, cw * 2, 0);
+        rc = make_tmap_2d(&tmC, g.y, (uint64_t)g.w_rows_pad, (uint64_t)p.M, (uint64_t)g.ldy * 2, cw, 32, cw * 2, 0);
         if (rc) return rc;
         p.flags |= CONV_F_TMA_OUT;
         if (!g_slab_stats) p.flags |= CONV_F_ACC_STATS;
     }
-    if (!g_early_release) p.flags |= CONV_F_LATE_RELEASE;
     return pair ? launch_conv_pair(tmA, tmB, tmC, p, st) : launch_conv_tc(tmA, tmB, tmC, p, st);
 }
 
@@ -392,9 +372,6 @@ int cy4_set_option(const char *name, int value)
     if (!strcmp(name, "ew_bwd_blocks_per_sm")) { CY4_CHECK_ARG(value >= 1 && value <= 32, "ew_bwd_blocks_per_sm must be in 1..32"); g_ew_bwd_bpsm = value; return 0; }
     if (!strcmp(name, "ew_carveout")) { g_ew_carveout = value ? 1 : 0; return 0; }
     if (!strcmp(name, "dgrad_interleave")) { g_dgrad_interleave = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "early_acc_release")) { g_early_release = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "group_store")) { g_group_store = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "b_resident")) { g_b_resident = value ? 1 : 0; return 0; }
     if (!strcmp(name, "slab_stats")) { g_slab_stats = value ? 1 : 0; return 0; }
     if (!strcmp(name, "conv_pair")) { g_conv_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "debug")) { g_debug = value; return 0; }      // bottleneck experiments: results are garbage

@@ -176,19 +176,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&ctl->tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * p.block_n;
-            const int nchunks = p.block_n / 32;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = 0; c < p.block_n / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c * 32, v);
                 tmem_ld_wait();
-                if (c == nchunks - 1 && !(p.flags & CONV_F_LATE_RELEASE)) {
-                    // The accumulator stage is free as soon as its LAST columns are in registers: hand it back to the MMA warp
-                    // here, not after the store / statistics work below.  Narrow, short-K tiles (N = 32..64, K = 32..128) are
-                    // bound by exactly this round trip: two accumulator stages per epilogue latency.
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);     // the leader's MMA warp owns the accumulator hand-over
-                }
                 const int n0 = n_blk * p.block_n + c * 32;
                 float f[32];
 #pragma unroll
@@ -299,11 +290,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
-            if (p.flags & CONV_F_LATE_RELEASE) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);     // the leader's MMA warp owns the accumulator hand-over
             acc_phase ^= 1;
         }
     }

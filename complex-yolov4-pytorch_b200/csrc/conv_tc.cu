@@ -41,7 +41,7 @@ constexpr int kSmemBytes = kCtlOffset + 1024 /*align*/ + kCtlBytes + 2 * kMaxSta
 constexpr uint32_t kTmemCols = 512;
 
 struct SmemCtl {
-    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], bres_full;
+    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
@@ -88,12 +88,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The TMA -> MMA round trip is ~1.5-2 us; a slot only holds 12..48 KB, so narrow / small-K layers need
     // many more slots in flight than the 4 that fit for the 128x256x64 tile (measured).
     const int nst = p.stages, kps = p.kps;
-    // Resident weights (p.bres_bytes > 0: narrow layers with one n tile whose whole packed weight matrix is <= 80 KB): every k-block
-    // of B is loaded ONCE per CTA into the head of the stage region and the pipeline slots carry activations only -- the producer
-    // thread issues one bulk-tensor load per k-block instead of two (these layers are bound by its issue loop).
-    const bool bres = p.bres_bytes > 0;
-    uint8_t *sA = smem + p.bres_bytes;
-    uint8_t *sB = bres ? smem : sA + nst * kps * p.a_stage;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + nst * kps * p.a_stage;
     uint8_t *sOut = smem + kStages * (kAStageBytes + kBStageBytes);
     SmemCtl *ctl = (SmemCtl *)(smem + kCtlOffset);
     float *sstat = (float *)(smem + kCtlOffset + kCtlBytes);     // [2][kMaxStatCh]
@@ -122,7 +118,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.flags & CONV_F_TMA_OUT) prefetch_tmap(&tmC);
         for (int s = 0; s < nst; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], cs); }
         for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tmem_full[s], 1); mbar_init(&ctl->tmem_empty[s], 4); }
-        mbar_init(&ctl->bres_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(&ctl->tmem_base);
@@ -139,12 +134,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             PPROBE_DECL;
             int stage = 0; uint32_t phase = 0;
             const int b_rows = p.block_n / cs;                 // weight rows this CTA fetches (and multicasts)
-            if (bres) {                                        // the whole weight matrix, once: k-block (tap, cc) at index tap * cin_chunks + cc
-                mbar_expect_tx(&ctl->bres_full, (uint32_t)(p.ntaps * p.cin_chunks) * b_bytes);
-                for (int tp = 0; tp < p.ntaps; ++tp)
-                    for (int c2 = 0; c2 < p.cin_chunks; ++c2)
-                        tma_load_2d(&tmB, &ctl->bres_full, sB + (tp * p.cin_chunks + c2) * p.b_stage, p.tap_kofs[tp] + c2 * p.kchunk, 0);
-            }
             for (int t = unit0; t < units; t += unit_step) {
                 int cls, tt;
                 unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt);
@@ -163,7 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     PPROBE_ACC(0);
                     if (CY4_DBG == 2 || CY4_DBG == 3 || CY4_DBG == 6) { mbar_expect_tx(&ctl->full[stage], 0); if (++stage == nst) { stage = 0; phase ^= 1; } continue; }
-                    mbar_expect_tx(&ctl->full[stage], (uint32_t)cnt * (a_bytes + (bres ? 0u : b_bytes)));
+                    mbar_expect_tx(&ctl->full[stage], (uint32_t)cnt * (a_bytes + b_bytes));
                     for (int j = 0; j < cnt; ++j) {
                         const int slot = stage * kps + j;
                         if (p.a_mode == 1)
@@ -171,8 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                (uint16_t)p.tap_ow[tap], (uint16_t)p.tap_oh[tap]);
                         else
                             tma_load_2d(&tmA, &ctl->full[stage], sA + slot * p.a_stage, cc * p.kchunk, m0);
-                        if (bres) {
-                        } else if (cs > 1)
+                        if (cs > 1)
                             tma_load_2d_mc(&tmB, &ctl->full[stage], sB + slot * p.b_stage + crank * b_rows * p.kchunk * 2,
                                            p.tap_kofs[tap] + cc * p.kchunk, n_blk * p.block_n + crank * b_rows, cmask);
                         else
@@ -195,7 +183,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_step = (uint32_t)p.a_stage >> 4, b_step = (uint32_t)p.b_stage >> 4;
         const bool k64 = p.kchunk == 64;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        if (bres) { mbar_wait(&ctl->bres_full, 0); tc_fence_after(); }       // the resident weights have landed
         PROBE_DECL;
         for (int t = unit0; t < units; t += unit_step) {
             PROBE_T0;
@@ -206,7 +193,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int cls, tt_;
             unit_decode(t, cls_units, ncls, p.cls_interleave, unit_step, cls, tt_);
             const int num_kb = (ncls > 1 ? p.cls_ntap[cls] : p.ntaps) * p.cin_chunks;
-            const int kb0 = (ncls > 1 ? p.cls_tap0[cls] : 0) * p.cin_chunks;    // first k-block of this tile's tap class
             for (int g0 = 0; g0 < num_kb; g0 += kps) {
                 const int cnt = min(kps, num_kb - g0);
                 PROBE_T0;
@@ -217,8 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (elect_one()) {
                     // descriptor low words advance by whole slots (addresses are 1024-aligned and < 256 KB, so the
                     // 14-bit address field never carries): one multiply-add per operand per k-block
-                    uint32_t a_lo = a_lo0 + (uint32_t)(stage * kps) * a_step;
-                    uint32_t b_lo = b_lo0 + (uint32_t)(bres ? kb0 + g0 : stage * kps) * b_step;     // resident: k-block index of the launch
+                    uint32_t a_lo = a_lo0 + (uint32_t)(stage * kps) * a_step, b_lo = b_lo0 + (uint32_t)(stage * kps) * b_step;
                     for (int j = 0; j < cnt; ++j, a_lo += a_step, b_lo += b_step) {
                         if (CY4_DBG != 1 && CY4_DBG != 3 && CY4_DBG != 6) {
                             umma_f16_lohi(d_tmem, a_lo, dhi, b_lo, dhi, idesc, (g0 + j) != 0);
@@ -270,19 +255,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&ctl->tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * p.block_n;
-            const int nchunks = p.block_n / 32;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = 0; c < p.block_n / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c * 32, v);
                 tmem_ld_wait();
-                if (c == nchunks - 1 && !(p.flags & CONV_F_LATE_RELEASE)) {
-                    // The accumulator stage is free as soon as its LAST columns are in registers: hand it back to the MMA warp
-                    // here, not after the store / statistics work below.  Narrow, short-K tiles (N = 32..64, K = 32..128) are
-                    // bound by exactly this round trip: two accumulator stages per epilogue latency.
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
-                }
                 const int n0 = n_blk * p.block_n + c * 32;
                 float f[32];
 #pragma unroll
@@ -298,22 +274,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // (32 columns = 64-byte rows, 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3)
                     // Narrow layers are bound by the TMA-store round trip of this slab, so they rotate through
                     // up to 4 slabs per warp (extra slabs live at the tail of the 192 KB stage region).
-                    // Group store (CONV_F_GROUP_STORE, narrow tiles): the TMA unit handles a bulk-tensor INSTRUCTION every few hundred
-                    // cycles whatever its size, and a 128 x 32 tile with one or two k-blocks issues 2-4 loads but 4 stores of 2 KB.
-                    // The four warps of an epilogue group lay their slabs out in row order (8 KB), meet at a named barrier, and ONE
-                    // thread stores the 128 rows.  Slab reuse: slab (c mod S) was last read by the store of chunk c - S; the issuer
-                    // waits for it (at most S - 2 younger stores pending) before it arrives at the barrier of chunk c - 1, which
-                    // every warp passes before it writes chunk c.
-                    const bool gstore = (p.flags & CONV_F_GROUP_STORE) != 0;
-                    uint8_t *blk = slab_i == 0 ? sOut : smem + kStages * (kAStageBytes + kBStageBytes) - slab_i * kOutStageBytes;
-                    uint8_t *gslab = blk + group * (4 * 32 * 64);
-                    uint8_t *slab = gstore ? gslab + quarter * (32 * 64) : blk + (warp - 2) * (32 * 64);
+                    uint8_t *slab = (slab_i == 0 ? sOut : smem + kStages * (kAStageBytes + kBStageBytes) - slab_i * kOutStageBytes) + (warp - 2) * (32 * 64);
                     const int cw = 32;
                     const int sub = 0;
-                    if (!gstore) {
-                        if (lane == 0) tma_store_wait_read_n(p.slab_bufs - 1);   // the store that used this slab has read it
-                        __syncwarp();
-                    }
+                    if (lane == 0) tma_store_wait_read_n(p.slab_bufs - 1);   // the store that used this slab has read it
+                    __syncwarp();
                     if (++slab_i == p.slab_bufs) slab_i = 0;
                     const int rowbytes = cw * 2;
                     const int xr = (lane >> 1) & 3;
@@ -325,16 +290,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int chunk = (sub + i) >> 3;            // 16-byte chunk index inside the row
                         *(uint4 *)(slab + lane * rowbytes + ((chunk ^ xr) << 4)) = o;
                     }
-                    fence_proxy_async();
-                    if (gstore) {
-                        named_bar_sync(1 + group, 128);
-                        if (quarter == 0 && lane == 0) {
-                            if (p.flags & CONV_F_ACCUM) tma_reduce_add_2d(&tmC, gslab, n_blk * p.block_n + c * 32, m_blk * kBlockM);
-                            else tma_store_2d(&tmC, gslab, n_blk * p.block_n + c * 32, m_blk * kBlockM);
-                            tma_store_commit();
-                            tma_store_wait_read_n(p.slab_bufs - 2);
-                        }
-                    } else {
+                    if (sub + 32 == cw) {                            // slab complete
+                        fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
                             if (p.flags & CONV_F_ACCUM) tma_reduce_add_2d(&tmC, slab, n_blk * p.block_n + c * 32 - sub, m_blk * kBlockM + quarter * 32);
@@ -435,11 +392,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            if (p.flags & CONV_F_LATE_RELEASE) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
             acc_phase ^= 1;
         }
     }

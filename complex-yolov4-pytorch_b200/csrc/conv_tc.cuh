@@ -11,8 +11,6 @@ enum : uint32_t {
     CONV_F_STATS = 2u,     // accumulate per-channel sum / sum^2 of the fp32 accumulators
     CONV_F_ACCUM = 4u,     // y += result (fp16 read-modify-write), used by dgrad into shared grads
     CONV_F_TMA_OUT = 16u,  // internal: fp16 tile staged in swizzled smem and written with TMA stores
-    CONV_F_GROUP_STORE = 128u, // internal: ONE TMA store of 128 rows per tile chunk (issued for the 4 epilogue warps of a group) instead of four of 32 rows
-    CONV_F_LATE_RELEASE = 64u, // internal (option early_acc_release=0): hand the TMEM accumulator back after the whole epilogue of the tile
     CONV_F_ACC_STATS = 32u,// internal (option slab_stats=0): statistics by reduce-scatter over the fp32 accumulators even when a slab is staged
 };
 
@@ -41,7 +39,6 @@ struct ConvKParams {
     int debug;                   // 1: skip MMAs, 2: skip TMA loads (bottleneck experiments)
     int stages, a_stage, b_stage;   // pipeline depth and per-stage bytes (the 192 KB stage region is split to fit)
     int kps;                     // k-blocks per pipeline slot (one barrier round trip per kps k-blocks)
-    int bres_bytes;              // > 0: ALL weight k-blocks of the launch stay resident in the first bres_bytes of the stage region (1-CTA kernel, one n tile)
     int slab_bufs;               // output slabs per epilogue warp (1, 2 or 4): TMA-store latency hiding for narrow layers
     int ab_fmt;                  // 0 fp16, 1 bf16
     // im2col base-pixel space: pixel m -> (img, pi, qi) over Po x Qo ; TMA base = (qi*tstride + lower_w, ...)

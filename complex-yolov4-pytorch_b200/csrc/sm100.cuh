@@ -128,16 +128,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, const vo
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// wait until at most `pending` (0..3) of this thread's bulk store groups are still reading shared memory
+// wait until at most `pending` (0, 1 or 3) of this thread's bulk store groups are still reading shared memory
 __device__ __forceinline__ void tma_store_wait_read_n(int pending)
 {
     if (pending >= 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-    else if (pending == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
     else if (pending >= 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
-// named barrier over `nthreads` threads (whole warps) of the CTA; id 0 is __syncthreads'
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------

@@ -181,7 +181,6 @@ class Darknet(nn.Module):
         self.bn_shifted_stats = True    # training: BN statistics summed about the previous step's batch mean (no E[y^2]-E[y]^2 cancellation)
         self.engine_allreduce = False   # True (set by models.model_utils.make_data_parallel): the engine averages gradients over the ranks
                                         # itself, overlapped with backward; DDP then carries a no-op communication hook
-        self.graph_allreduce = 1        # with use_cuda_graph: capture those NCCL all-reduces into the backward graph (0: run them after the replay)
         self.allreduce_groups = 6       # number of gradient groups of that exchange
         self.fuse_bn_backward = 0       # 0 (default): BN/activation backward as two bandwidth-bound passes.  1 / 2: the dgrad epilogue of a
                                         # tensor's last gradient writer does the first pass (cy4_conv_dgrad_fused) on long-K layers / wherever

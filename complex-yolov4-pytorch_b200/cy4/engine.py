@@ -208,7 +208,7 @@ class StepEngine:
             return plan.forward(x, targets, model.use_giou_loss)
         gs = plan.graph_state
         key = (int(targets.shape[0]), bool(model.use_giou_loss), int(getattr(model, "wgrad_overlap", 2)), int(getattr(model, "dy_ring", 4)),
-               int(getattr(model, "wgrad_priority", 0)), int(getattr(model, "graph_allreduce", 1)))
+               int(getattr(model, "wgrad_priority", 0)))
         if gs is None or gs["key"] != key:
             gs = plan.graph_state = dict(key=key, eager=0, fwd=None, bwd=None, x=torch.empty_like(x, dtype=torch.float32),
                                          tg=torch.empty(targets.shape, device=x.device, dtype=torch.float32),
@@ -244,14 +244,14 @@ class StepEngine:
             gs["bwd"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gs["bwd"]):
                 plan.backward(gs["g"])                   # (its return value -- copies made inside the capture -- is not used)
-            gs["ar_in_graph"] = bool(getattr(plan, "ar_in_graph", False))     # the gradient exchange is part of the graph
             gs["bwd_launches"] = int(self.L.cy4_kernel_launches(0)) - n0
         gs["bwd"].replay()
         self.L.cy4_note_graph_replay(gs["bwd_launches"])
         # The gradient base tensors are static graph memory.  With the engine-side exchange (models.model_utils
-        # overlap_gradient_exchange) the grouped NCCL all-reduces are normally part of the captured backward graph
-        # (model.graph_allreduce); otherwise the bases are averaged over the ranks here, after the replay.
-        if getattr(self.model, "engine_allreduce", False) and not gs.get("ar_in_graph", False):
+        # overlap_gradient_exchange: DDP carries a no-op hook) they are averaged over the ranks here, after the replay --
+        # not overlapped in this mode, but the ~850 launches of the step cost the host nothing, which is what bounds
+        # multi-rank steps (bench.py host_enqueue_ms_per_step).
+        if getattr(self.model, "engine_allreduce", False):
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 for b in plan._grad_bases:
@@ -895,17 +895,11 @@ class Plan:
 
         # gradient exchange done by the engine itself (model.engine_allreduce, set by models.model_utils.make_data_parallel
         # together with a no-op DDP communication hook): grouped, asynchronous, overlapped with the rest of backward
-        # Under CUDA-graph capture the same grouped all-reduces are captured INTO the backward graph (model.graph_allreduce, default
-        # on: NCCL collectives are capturable; the communicator has been used by the two eager steps that precede the capture), so
-        # the exchange overlaps the rest of backward in replay as well; graph_allreduce = 0 runs it after the replay instead.
         ar_groups, works = None, []
-        capturing = self.graph_state is not None and self.graph_state["fwd"] is not None
-        self.ar_in_graph = False
-        if getattr(model, "engine_allreduce", False) and (not capturing or int(getattr(model, "graph_allreduce", 1))):
+        if getattr(model, "engine_allreduce", False) and (self.graph_state is None or self.graph_state["fwd"] is None):   # (eager steps)
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 ar_groups = self._allreduce_groups()
-                self.ar_in_graph = capturing
 
         for ind in sorted(events, reverse=True):
             kind, r = events[ind]

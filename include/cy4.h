@@ -163,12 +163,6 @@ typedef struct cy4_conv_desc {
  *   carve-out (experiment: measured slower, kept for the record);
  * "dgrad_interleave" (0|1, default 1): merged stride-2 input gradients whose dY exceeds 64 MB walk the four output-parity classes
  *   of a tile in neighbouring work units (three of the four dY reads hit L2) instead of class after class (four DRAM passes);
- * "b_resident" (0|1, default 1): 1-CTA conv launches with one n tile and <= 80 KB of packed weights load ALL weight k-blocks once per CTA
- *   into shared memory; the pipeline slots then carry activations only (half the bulk-tensor loads of the producer thread);
- * "group_store" (0|1, default 1): narrow tiles of the 1-CTA conv kernel (N tile <= 64) issue ONE 128-row TMA store per tile chunk for the
- *   four warps of an epilogue group instead of four 32-row stores (the TMA unit is instruction-rate bound on these layers);
- * "early_acc_release" (0|1, default 1): the conv epilogue hands a TMEM accumulator stage back to the MMA warp right after its last
- *   tcgen05.ld instead of after the tile's store / statistics work (narrow short-K tiles are bound by that round trip);
  * "slab_stats" (0|1, default 1): CY4_CONV_STATS sums are read off the staged fp16 output slab (the statistics of the STORED tensor,
  *   ~100 instructions per 32x32 slab) instead of a shuffle reduce-scatter over the fp32 accumulators (~400, a dependent chain);
  * "debug": bottleneck experiments, honoured only by -DCY4_PROBE side builds (tools/probe_pipeline.py). */

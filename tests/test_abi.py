@@ -58,7 +58,7 @@ def test_set_option_names_and_ranges():
     L = _lib.lib()
     ok = [(b"conv_cluster", 2), (b"conv_cluster", 1), (b"wgrad_cluster", 2), (b"wgrad_cluster", 1), (b"tma_store", 0), (b"tma_store", 1),
           (b"kblocks_per_slot", 1), (b"kblocks_per_slot", 4), (b"conv_pair", 0), (b"conv_pair", 1), (b"conv1x1_matrix", 1), (b"conv1x1_matrix", 0),
-          (b"slab_stats", 0), (b"slab_stats", 1), (b"dgrad_interleave", 0), (b"dgrad_interleave", 1), (b"early_acc_release", 0), (b"early_acc_release", 1), (b"group_store", 0), (b"group_store", 1), (b"b_resident", 0), (b"b_resident", 1), (b"ew_carveout", 1), (b"ew_carveout", 0), (b"pdl", 1), (b"pdl", 0), (b"ew_fwd_blocks_per_sm", 6), (b"ew_fwd_blocks_per_sm", 3), (b"ew_bwd_blocks_per_sm", 6), (b"ew_bwd_blocks_per_sm", 2), (b"debug", 0)]
+          (b"slab_stats", 0), (b"slab_stats", 1), (b"dgrad_interleave", 0), (b"dgrad_interleave", 1), (b"ew_carveout", 1), (b"ew_carveout", 0), (b"pdl", 1), (b"pdl", 0), (b"ew_fwd_blocks_per_sm", 6), (b"ew_fwd_blocks_per_sm", 3), (b"ew_bwd_blocks_per_sm", 6), (b"ew_bwd_blocks_per_sm", 2), (b"debug", 0)]
     for name, value in ok:
         assert L.cy4_set_option(name, value) == 0, (name, value)
     for name, value in [(b"no_such_option", 1), (b"wgrad_cluster", 3), (b"conv_cluster", 3)]:
