@@ -368,7 +368,7 @@ def test_overlapped_wgrad_under_cuda_graph_replay():
     # (two trainings from the same state drift apart through the atomically summed statistics, DESIGN.md section 5: the first
     #  step agrees closely, the ones after an optimizer update to the measured run-to-run spread)
     for i, (a, b) in enumerate(zip(runs[0], runs[2])):
-        assert abs(a - b) <= (1e-3 if i == 0 else 3e-2) * abs(a), (runs[0], runs[2])
+        assert abs(a - b) <= (2e-3 if i == 0 else 3e-2) * abs(a), (runs[0], runs[2])
 
 
 def test_programmatic_dependent_launch_gives_the_same_step():
@@ -399,7 +399,7 @@ def test_programmatic_dependent_launch_gives_the_same_step():
         print("losses plain", runs[(0, False)], "pdl eager", runs[(1, False)], "pdl graph", runs[(1, True)])
         for key in ((1, False), (1, True)):      # (same drift as any two runs: DESIGN.md section 5)
             for i, (a, b) in enumerate(zip(runs[(0, False)], runs[key])):
-                assert abs(a - b) <= (1e-3 if i == 0 else 3e-2) * abs(a), (key, runs)
+                assert abs(a - b) <= (2e-3 if i == 0 else 3e-2) * abs(a), (key, runs)
         # gradients on ONE forward state
         torch.manual_seed(1)
         model = Darknet(netdefs.cfg_path("complex_yolov4"), True).cuda().train()

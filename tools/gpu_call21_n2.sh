@@ -1,5 +1,7 @@
 #!/bin/bash
-# call 21 (2 GPUs): the gradient exchange captured into the backward graph
+# call 21 (2 GPUs): the gradient exchange captured into the backward graph.
+# HISTORICAL: ran at commit 79e7e6c (model.graph_allreduce existed there); the in-graph exchange hung and was reverted,
+# so `--model-opt graph_allreduce=0` and the graph-replay DDP test no longer exist at HEAD.
 mkdir -p gpurun_out
 O=gpurun_out
 timeout 900 python -m pytest tests/test_gpu_ddp.py -q -m gpu -s > $O/c21_pytest_ddp.log 2>&1; echo "ddp tests rc $?"; tail -6 $O/c21_pytest_ddp.log
