@@ -251,6 +251,7 @@ def run_ours(args):
             # ---- roofline pass: CUDA-event timing of every tensor-core conv launch for 2 steps
             plan = net._engine.plan
             net.use_cuda_graph = False          # events around individual launches need eager launches
+            net.engine_allreduce = False        # rank 0 runs this alone: the engine must not issue its gradient all-reduces here
             plan.prof = []
             for _ in range(2):                  # on the bare module: no collective may run on rank 0 alone
                 l_, _o = net(x, tg)
