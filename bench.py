@@ -247,7 +247,12 @@ def run_ours(args):
         ms_per_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total / 1e3)
         roof, giou, nxt, fwd_ms = None, None, None, None
-        if not args.no_roofline:
+
+        def extras():
+            """Rank 0 only, after the timed regions: per-launch roofline pass, forward-only timing, rotated-GIoU microbench,
+            the "next" rows.  Guarded as a whole below: a failure here must never cost the headline line (nor leave the other
+            ranks waiting at the final barrier for longer than it takes to report it)."""
+            roof, giou, nxt, fwd_ms = None, None, None, None
             # ---- roofline pass: CUDA-event timing of every tensor-core conv launch for 2 steps
             plan = net._engine.plan
             net.use_cuda_graph = False          # events around individual launches need eager launches
@@ -370,6 +375,13 @@ def run_ours(args):
                                           "algorithmic_GBps": round(B * (120000 * 16 + 3 * 608 * 608 * 4) / (t_ / 1e3) / 1e9, 1)}
             except Exception as e:      # noqa: BLE001
                 nxt["f3_lidar_to_bev"] = {"error": repr(e)[:300]}
+            return roof, giou, nxt, fwd_ms
+
+        if not args.no_roofline:
+            try:
+                roof, giou, nxt, fwd_ms = extras()
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write("bench: the roofline / microbench pass failed (%r); the headline line is unaffected\n" % (e,))
         result = {
             "metric": "BEV-images/sec training step (bs=32, 608x608)", "value": round(value, 2), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
